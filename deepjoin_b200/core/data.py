@@ -1,0 +1,75 @@
+"""The per-iteration sampler of the latent optimisation (reference core/data.py:15-73,122-176).
+
+``select_samples`` keeps the reference's signature and consumes numpy's GLOBAL RNG in exactly
+the reference's order, so a seeded run draws the same mini-batches.  ``select_sample_indices``
+is the same procedure on row indices only (what the device loop needs): identical RNG calls,
+identical rows, without copying 300k x 7 values per iteration."""
+import numpy as np
+
+from . import errors
+
+
+def _uniform_ratio_rows(n_pts, uniform_ratio, randomize=True):
+    """Row ids kept by select_uniform_ratio_samples (core/data.py:122-176), in output order."""
+    half = int(n_pts / 2)
+    if uniform_ratio != 0.5:
+        max_can_select = half
+        surface_ends_at = half
+        if uniform_ratio > 0.5:
+            k = int((max_can_select * (1 - uniform_ratio)) / uniform_ratio)
+            sel = np.random.choice(max_can_select, size=(k), replace=False)
+            rows = np.concatenate([sel, np.arange(surface_ends_at, surface_ends_at + max_can_select)])
+        else:
+            k = int((max_can_select * uniform_ratio) / (1 - uniform_ratio))
+            sel = np.random.choice(max_can_select, size=(k), replace=False) + surface_ends_at
+            rows = np.concatenate([np.arange(max_can_select), sel])
+    else:
+        rows = np.arange(n_pts)
+    if randomize:
+        rows = rows[np.random.permutation(rows.shape[0])]
+    return rows
+
+
+def select_sample_indices(values, num_samples=None, uniform_ratio=0.5):
+    """Indices such that ``pts[idx], values[idx]`` equals the reference's
+    ``select_samples(pts, values, num_samples, uniform_ratio)`` (single value column)."""
+    values = np.asarray(values)
+    if values.ndim == 2:
+        if values.shape[1] != 1:
+            raise NotImplementedError("multi-shape value columns")
+        values = values[:, 0]
+    rows = _uniform_ratio_rows(values.shape[0], uniform_ratio) if uniform_ratio is not None else np.arange(values.shape[0])
+    d = values[rows]
+    s = d.shape[0] if num_samples is None else num_samples
+    pos_inds = np.where(d > 0)[0]
+    neg_inds = np.where(d <= 0)[0]
+    pos_num, neg_num = (s // 2), (s - (s // 2))
+    if len(neg_inds) > neg_num:
+        start_ind = np.random.randint(len(neg_inds) - neg_num)
+        neg_picked = neg_inds[start_ind: start_ind + neg_num]
+    else:
+        try:
+            neg_picked = np.random.choice(neg_inds, neg_num)
+        except ValueError:
+            raise errors.NoSamplesError
+    if len(pos_inds) > pos_num:
+        start_ind = np.random.randint(len(pos_inds) - pos_num)
+        pos_picked = pos_inds[start_ind: start_ind + pos_num]
+    else:
+        try:
+            pos_picked = np.random.choice(pos_inds, pos_num)
+        except ValueError:
+            raise errors.NoSamplesError
+    return rows[np.concatenate([pos_picked, neg_picked])]
+
+
+def select_samples(pts, values, num_samples=None, uniform_ratio=0.5):
+    """core/data.py:15-73 (one value column)."""
+    idx = select_sample_indices(values, num_samples, uniform_ratio)
+    return pts[idx, :], values[idx, :]
+
+
+def clamp_samples(data, clamp_dist, skip_cols=0):
+    """core/data.py:207-212."""
+    data[:, skip_cols:] = np.clip(data[:, skip_cols:], -clamp_dist, clamp_dist)
+    return data

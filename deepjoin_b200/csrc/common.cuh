@@ -1,0 +1,88 @@
+// Shared host-side plumbing for the deepjoin_b200 C ABI (error reporting, launch counter).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <atomic>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/deepjoin_b200.h"
+
+namespace dj {
+
+inline std::string& last_error_ref() {
+  static thread_local std::string s;
+  return s;
+}
+
+inline int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  last_error_ref() = buf;
+  return code;
+}
+
+inline std::atomic<int64_t>& launch_counter() {
+  static std::atomic<int64_t> c{0};
+  return c;
+}
+
+#define DJ_CUDA(expr)                                                                          \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return dj::fail(DJ_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+#define DJ_LAUNCHED()                                                                          \
+  do {                                                                                         \
+    dj::launch_counter().fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess)                                                                     \
+      return dj::fail(DJ_ERR_CUDA, "%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace dj

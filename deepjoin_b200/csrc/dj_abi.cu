@@ -1,0 +1,713 @@
+// C ABI of deepjoin_b200 (see include/deepjoin_b200.h): weight packing, launch orchestration.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include "common.cuh"
+#include "mlp_simt.cuh"
+#include "mlp_tc.cuh"
+#include "mc.cuh"
+#include "sampler.cuh"
+
+using namespace dj;
+
+// ====================================================================== pack
+struct DjPack {
+  DjNetDesc desc{};
+  int device = 0;
+  int num_sms = 0;
+  int L = 0, Lb = 0, H = 512;
+  int K3 = 0;  // width of the h part of the re-injection layer's input (hidden - (L+3))
+  // fp32 folded weights on the device, nn.Linear layout [out,in]
+  std::vector<float*> fW, fB, hW, hB;
+  std::vector<int> f_out, f_in, h_out, h_in;
+  float* fWx = nullptr;  // [H, K3+3] = [W_li[:, :K3] | W_li[:, K3+L : K3+L+3]] (fp32 forward of the re-injection layer)
+  // tensor-core path
+  uint8_t* stream[2] = {nullptr, nullptr};
+  float* bias_dev = nullptr;
+  tc::TcNet nets[2];
+  // per-call shape constants + device error word
+  float4* tables = nullptr;
+  unsigned int* err = nullptr;
+  simt::FoldParams fold{};
+  // workspaces (grow only)
+  DevBuf ws_fwd, ws_lat, ws_host, ws_vol;
+  bool tc_attr_set = false;
+};
+
+static void free_pack(DjPack* p) {
+  if (!p) return;
+  DeviceGuard g(p->device);
+  for (auto v : {&p->fW, &p->fB, &p->hW, &p->hB})
+    for (float* q : *v)
+      if (q) cudaFree(q);
+  if (p->fWx) cudaFree(p->fWx);
+  for (int i = 0; i < 2; i++)
+    if (p->stream[i]) cudaFree(p->stream[i]);
+  if (p->bias_dev) cudaFree(p->bias_dev);
+  if (p->tables) cudaFree(p->tables);
+  if (p->err) cudaFree(p->err);
+  p->ws_fwd.release();
+  p->ws_lat.release();
+  p->ws_host.release();
+  p->ws_vol.release();
+  delete p;
+}
+
+// one [rows x 64] bf16 tile, K-major, 128-byte swizzle (the layout the UMMA descriptor
+// umma_desc_sw128_kmajor describes): element (r, k) at r*128 + ((k/8) ^ (r%8))*16 + (k%8)*2
+static void pack_tile(const float* W, int ldw, int n_real, int k_real, int n0, int k0, int rows, uint8_t* dst) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      const int gn = n0 + r, gk = k0 + k;
+      const float v = (gn < n_real && gk < k_real) ? W[(size_t)gn * ldw + gk] : 0.f;
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      memcpy(dst + off, &b, 2);
+    }
+}
+
+extern "C" int dj_abi_version(void) { return DJ_ABI_VERSION; }
+extern "C" const char* dj_last_error(void) { return last_error_ref().c_str(); }
+extern "C" int64_t dj_launch_count(int reset) {
+  return reset ? launch_counter().exchange(0) : launch_counter().load();
+}
+extern "C" int dj_pack_device(const DjPack* p) { return p ? p->device : -1; }
+
+extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const float* const* f_b,
+                              const float* const* h_w, const float* const* h_b, int device, DjPack** out) {
+  if (!d || !f_w || !f_b || !h_w || !h_b || !out) return fail(DJ_ERR_INVALID, "dj_pack_create: null argument");
+  *out = nullptr;
+  if (d->hidden != 512) return fail(DJ_ERR_UNSUPPORTED, "hidden width %d (only 512 is supported)", d->hidden);
+  if (d->f_layers < 4 || d->f_layers > tc::MAX_LAYERS || d->h_layers < 3 || d->h_layers > tc::MAX_LAYERS)
+    return fail(DJ_ERR_UNSUPPORTED, "layer counts f=%d h=%d outside the supported range", d->f_layers, d->h_layers);
+  if (d->latent_in < 2 || d->latent_in > d->f_layers - 2)
+    return fail(DJ_ERR_UNSUPPORTED, "latent_in=%d must name a hidden layer >= 2", d->latent_in);
+  const int L = d->latent_size, Lb = d->tool_latent_size, H = d->hidden;
+  const int K3 = H - (L + 3);
+  if (L < 1 || Lb < 1 || K3 < 64) return fail(DJ_ERR_UNSUPPORTED, "latent sizes %d/%d not supported", L, Lb);
+  int ndev = 0;
+  DJ_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DJ_ERR_INVALID, "device %d out of range", device);
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  DJ_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(DJ_ERR_UNSUPPORTED, "device sm_%d%d: this library is built for sm_100a only", prop.major, prop.minor);
+
+  DjPack* p = new DjPack();
+  p->desc = *d;
+  p->device = device;
+  p->num_sms = prop.multiProcessorCount;
+  p->L = L; p->Lb = Lb; p->H = H; p->K3 = K3;
+  auto bail = [&](int code) { free_pack(p); return code; };
+
+  // ---- layer shapes as Decoder.__init__ builds them (decoder :60-131)
+  for (int l = 0; l < d->f_layers; l++) {
+    p->f_in.push_back(l == 0 ? L + 3 : H);
+    p->f_out.push_back(l == d->f_layers - 1 ? 5 : (l + 1 == d->latent_in ? K3 : H));
+  }
+  for (int l = 0; l < d->h_layers; l++) {
+    p->h_in.push_back(l == 0 ? Lb + 3 : H);
+    p->h_out.push_back(l == d->h_layers - 1 ? 5 : H);
+  }
+  auto upload = [&](const float* src, size_t n, float** dst) -> cudaError_t {
+    cudaError_t e = cudaMalloc((void**)dst, n * sizeof(float));
+    if (e != cudaSuccess) return e;
+    return cudaMemcpy(*dst, src, n * sizeof(float), cudaMemcpyHostToDevice);
+  };
+#define DJ_TRY(expr)                                                                                   \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) return bail(fail(DJ_ERR_CUDA, "%s -> %s", #expr, cudaGetErrorString(_e)));  \
+  } while (0)
+  p->fW.assign(d->f_layers, nullptr); p->fB.assign(d->f_layers, nullptr);
+  p->hW.assign(d->h_layers, nullptr); p->hB.assign(d->h_layers, nullptr);
+  for (int l = 0; l < d->f_layers; l++) {
+    DJ_TRY(upload(f_w[l], (size_t)p->f_out[l] * p->f_in[l], &p->fW[l]));
+    DJ_TRY(upload(f_b[l], (size_t)p->f_out[l], &p->fB[l]));
+  }
+  for (int l = 0; l < d->h_layers; l++) {
+    DJ_TRY(upload(h_w[l], (size_t)p->h_out[l] * p->h_in[l], &p->hW[l]));
+    DJ_TRY(upload(h_b[l], (size_t)p->h_out[l], &p->hB[l]));
+  }
+  const int li = d->latent_in;
+  {  // fp32 re-injection layer with the latent columns removed: [h (K3) | xyz (3)]
+    std::vector<float> wx((size_t)H * (K3 + 3));
+    for (int j = 0; j < H; j++) {
+      for (int k = 0; k < K3; k++) wx[(size_t)j * (K3 + 3) + k] = f_w[li][(size_t)j * H + k];
+      for (int k = 0; k < 3; k++) wx[(size_t)j * (K3 + 3) + K3 + k] = f_w[li][(size_t)j * H + K3 + L + k];
+    }
+    DJ_TRY(upload(wx.data(), wx.size(), &p->fWx));
+  }
+  // ---- latent fold descriptors (tables 0: lin0, 1: lin<latent_in>, 2: hnet_lin0)
+  p->fold.src[0] = {p->fW[0], p->fB[0], L + 3, 0, L, L, 0};
+  p->fold.src[1] = {p->fW[li], p->fB[li], H, K3, L, K3 + L, 0};
+  p->fold.src[2] = {p->hW[0], p->hB[0], Lb + 3, 0, Lb, Lb, L};
+  DJ_TRY(cudaMalloc((void**)&p->tables, 3 * 512 * sizeof(float4)));
+  DJ_TRY(cudaMalloc((void**)&p->err, sizeof(unsigned int)));
+  DJ_TRY(cudaMemset(p->err, 0, sizeof(unsigned int)));
+
+  // ---- tensor-core program + weight stream
+  std::vector<float> bias_host;
+  for (int net = 0; net < 2; net++) {
+    const int nl = net == 0 ? d->f_layers : d->h_layers;
+    const float* const* W = net == 0 ? f_w : h_w;
+    const float* const* B = net == 0 ? f_b : h_b;
+    const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
+    const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
+    tc::TcNet& N = p->nets[net];
+    memset(&N, 0, sizeof N);
+    N.n_layers = nl - 1;  // layer 0 runs on CUDA cores
+    N.l0_table = net == 0 ? 0 : 2;
+    N.head_leaky = net == 1;  // decoder :259-270
+    std::vector<uint8_t> blob;
+    int prev_n_chunks = 4;  // layer 0 writes all 8 k-chunks
+    for (int l = 1; l < nl; l++) {
+      tc::TcLayer& T = N.layers[l - 1];
+      const bool head = (l == nl - 1);
+      const bool reinj = (net == 0 && l == li);
+      const int n_real = outs[l];
+      const int k_real = reinj ? K3 : ins[l];
+      T.k_chunks = (int16_t)(2 * prev_n_chunks);
+      if (k_real > T.k_chunks * 64) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K=%d exceeds the previous layer's width", l, k_real));
+      T.n_chunks = (int16_t)(head ? 1 : (n_real + 127) / 128);
+      T.mma_n = (int16_t)(head ? 16 : 128);
+      T.kind = (int16_t)(head ? tc::KIND_HEAD : (reinj ? tc::KIND_HIDDEN_XYZ : tc::KIND_HIDDEN));
+      T.table = reinj ? 1 : 0;
+      T.stage_bytes = T.mma_n * 64 * 2;
+      T.bias_off = (int32_t)bias_host.size();
+      if (!reinj) {
+        for (int j = 0; j < 512; j++) bias_host.push_back(j < n_real ? B[l][j] : 0.f);
+      }
+      const int rows = T.mma_n;
+      for (int j = 0; j < T.n_chunks; j++)
+        for (int c = 0; c < T.k_chunks; c++) {
+          const size_t o = blob.size();
+          blob.resize(o + T.stage_bytes);
+          pack_tile(W[l], ins[l], n_real, k_real, j * rows, c * 64, rows, blob.data() + o);
+        }
+      prev_n_chunks = T.n_chunks;
+    }
+    DJ_TRY(cudaMalloc((void**)&p->stream[net], blob.size()));
+    DJ_TRY(cudaMemcpy(p->stream[net], blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    N.stream = p->stream[net];
+  }
+  DJ_TRY(upload(bias_host.data(), bias_host.size(), &p->bias_dev));
+#undef DJ_TRY
+  *out = p;
+  return DJ_OK;
+}
+
+extern "C" int dj_pack_destroy(DjPack* p) {
+  free_pack(p);
+  return DJ_OK;
+}
+
+// ====================================================================== forward
+struct GridSpec {
+  int on = 0;
+  int d0 = 0, d1 = 0, d2 = 0;
+  double stop = 0, offs = 0;
+  int64_t r_lo = 0;
+  double step(int d) const { return d > 1 ? stop / (double)(d - 1) : 0.0; }
+};
+
+static int check_err_word(DjPack* p, cudaStream_t st) {
+  unsigned int h = 0;
+  DJ_CUDA(cudaMemcpyAsync(&h, p->err, sizeof h, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaStreamSynchronize(st));
+  if (h) return fail(DJ_ERR_DEVICE, "device watchdog fired: 0x%08x", h);
+  return DJ_OK;
+}
+
+static int launch_fold(DjPack* p, const float* code_dev, cudaStream_t st) {
+  simt::fold_kernel<<<(3 * 512 * 32 + 255) / 256, 256, 0, st>>>(p->fold, code_dev, p->tables);
+  DJ_LAUNCHED();
+  return DJ_OK;
+}
+
+template <bool TB>
+static int launch_sgemm(const float* A, int lda, const float* B, int ldb, float* C, int ldc, int64_t M, int N, int K,
+                        const float* bias, int bstride, int act, float slope, const float* dsrc, int ldd, cudaStream_t st) {
+  dim3 grid((N + simt::BN - 1) / simt::BN, (unsigned)((M + simt::BM - 1) / simt::BM));
+  simt::sgemm_kernel<TB><<<grid, 256, 0, st>>>(A, lda, B, ldb, C, ldc, (int)M, N, K, bias, bstride, act, slope, dsrc, ldd);
+  DJ_LAUNCHED();
+  return DJ_OK;
+}
+
+// fp32 forward of both nets for n points.  fH[l] / hH[l]: output buffer of layer l ([n,512], ld 512);
+// yC / yT: [n,8].  Distinct buffers per layer when the activations are kept for the backward.
+static int fp32_forward(DjPack* p, const float* xyz, int64_t n, int net_mask, float* const* fH, float* const* hH,
+                        float* yC, float* yT, cudaStream_t st) {
+  const float slope = p->desc.slope;
+  const float* tabf = reinterpret_cast<const float*>(p->tables);
+  const int H = p->H, K3 = p->K3, li = p->desc.latent_in;
+  int rc;
+  if (net_mask & 1) {
+    const int nl = p->desc.f_layers;
+    if ((rc = launch_sgemm<true>(xyz, 3, tabf, 4, fH[0], H, n, H, 3, tabf + 3, 4, 1, slope, nullptr, 0, st))) return rc;
+    for (int l = 1; l < nl; l++) {
+      const float* in = fH[l - 1];
+      if (l == nl - 1) {
+        if ((rc = launch_sgemm<true>(in, H, p->fW[l], H, yC, 8, n, 5, H, p->fB[l], 1, 0, slope, nullptr, 0, st))) return rc;
+      } else if (l == li) {
+        simt::put_xyz_cols_kernel<<<ceil_div(n, 256), 256, 0, st>>>(xyz, fH[l - 1], H, K3, n);
+        DJ_LAUNCHED();
+        if ((rc = launch_sgemm<true>(in, H, p->fWx, K3 + 3, fH[l], H, n, H, K3 + 3, tabf + 4 * 512 + 3, 4, 1, slope, nullptr, 0, st))) return rc;
+      } else {
+        if ((rc = launch_sgemm<true>(in, H, p->fW[l], H, fH[l], H, n, p->f_out[l], H, p->fB[l], 1, 1, slope, nullptr, 0, st))) return rc;
+      }
+    }
+  }
+  if (net_mask & 2) {
+    const int nl = p->desc.h_layers;
+    const float* t2 = tabf + 2 * 4 * 512;
+    if ((rc = launch_sgemm<true>(xyz, 3, t2, 4, hH[0], H, n, H, 3, t2 + 3, 4, 1, slope, nullptr, 0, st))) return rc;
+    for (int l = 1; l < nl; l++) {
+      if (l == nl - 1) {
+        if ((rc = launch_sgemm<true>(hH[l - 1], H, p->hW[l], H, yT, 8, n, 5, H, p->hB[l], 1, 1, slope, nullptr, 0, st))) return rc;
+      } else {
+        if ((rc = launch_sgemm<true>(hH[l - 1], H, p->hW[l], H, hH[l], H, n, H, H, p->hB[l], 1, 1, slope, nullptr, 0, st))) return rc;
+      }
+    }
+  }
+  return DJ_OK;
+}
+
+static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, const GridSpec& G, int64_t n,
+                       const HeadCfg& head, int net_mask, int precision, float* out_dev, cudaStream_t st) {
+  if (n <= 0) return DJ_OK;
+  int rc;
+  if ((rc = launch_fold(p, code_dev, st))) return rc;
+  if (precision == DJ_PREC_BF16) {
+    if (!p->tc_attr_set) {
+      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      p->tc_attr_set = true;
+    }
+    tc::TcParams P;
+    memset(&P, 0, sizeof P);
+    P.nets[0] = p->nets[0];
+    P.nets[1] = p->nets[1];
+    P.net_mask = net_mask;
+    P.grid_mode = G.on;
+    P.bias = p->bias_dev;
+    P.tables = p->tables;
+    P.xyz = xyz_dev;
+    P.n = n;
+    P.d0 = G.d0; P.d1 = G.d1; P.d2 = G.d2;
+    P.step0 = G.step(G.d0); P.step1 = G.step(G.d1); P.step2 = G.step(G.d2);
+    P.stop = G.stop; P.offs = G.offs; P.r_lo = G.r_lo;
+    P.head = head;
+    P.out = out_dev;
+    P.err = p->err;
+    const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
+    const int grid = (int)std::min<int64_t>(ntiles, p->num_sms);
+    tc::tc_forward_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(P);
+    DJ_LAUNCHED();
+    return DJ_OK;
+  }
+  if (precision != DJ_PREC_FP32) return fail(DJ_ERR_INVALID, "unknown precision %d", precision);
+  // fp32: layer-by-layer SGEMMs over chunks, two ping-pong activation buffers
+  const int64_t CH = 65536;
+  const int64_t c = std::min(CH, n);
+  const size_t act = (size_t)c * 512 * sizeof(float);
+  const size_t need = 2 * act + 2 * (size_t)c * 8 * sizeof(float) + (size_t)c * 3 * sizeof(float);
+  DJ_CUDA(p->ws_fwd.reserve(need));
+  uint8_t* w = p->ws_fwd.as<uint8_t>();
+  float* bufA = reinterpret_cast<float*>(w);
+  float* bufB = reinterpret_cast<float*>(w + act);
+  float* yC = reinterpret_cast<float*>(w + 2 * act);
+  float* yT = yC + c * 8;
+  float* gx = yT + c * 8;
+  std::vector<float*> fH(p->desc.f_layers), hH(p->desc.h_layers);
+  for (int l = 0; l < p->desc.f_layers; l++) fH[l] = (l & 1) ? bufB : bufA;
+  for (int l = 0; l < p->desc.h_layers; l++) hH[l] = (l & 1) ? bufB : bufA;
+  for (int64_t s = 0; s < n; s += CH) {
+    const int64_t m = std::min(CH, n - s);
+    const float* xyz = xyz_dev ? xyz_dev + 3 * s : gx;
+    if (G.on) {
+      simt::grid_points_kernel<<<ceil_div(m, 256), 256, 0, st>>>(gx, m, G.r_lo + s, G.d0, G.d1, G.d2, G.step(G.d0),
+                                                                G.step(G.d1), G.step(G.d2), G.stop, G.offs);
+      DJ_LAUNCHED();
+      xyz = gx;
+    }
+    if ((rc = fp32_forward(p, xyz, m, net_mask, fH.data(), hH.data(), yC, yT, st))) return rc;
+    float* o = out_dev + (head.out_mode == OUT_ALL20 ? 20 * s : s);
+    simt::heads_kernel<<<ceil_div(m, 256), 256, 0, st>>>(head, (net_mask & 1) ? yC : nullptr, (net_mask & 2) ? yT : nullptr, 8, o, m);
+    DJ_LAUNCHED();
+  }
+  return DJ_OK;
+}
+
+static int net_mask_for(int use_net) { return use_net == 0 ? 1 : (use_net == 3 ? 2 : 3); }
+
+extern "C" int dj_query_points(DjPack* p, const float* code_dev, const float* xyz_dev, int64_t n, int use_net,
+                               int return_occ, int apply_sigmoid, int precision, float* out_dev, void* stream) {
+  if (!p || !code_dev || (!xyz_dev && n > 0) || (!out_dev && n > 0) || n < 0) return fail(DJ_ERR_INVALID, "dj_query_points: bad argument");
+  if (use_net < 0 || use_net > 3) return fail(DJ_ERR_BAD_NET, "Requested output from non-existent network: %d", use_net);
+  DeviceGuard g(p->device);
+  HeadCfg H{OUT_SINGLE, use_net, return_occ, apply_sigmoid, p->desc.slope};
+  return run_forward(p, code_dev, xyz_dev, GridSpec{}, n, H, net_mask_for(use_net), precision, out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dj_query_all(DjPack* p, const float* code_dev, const float* xyz_dev, int64_t n, int precision,
+                            float* out_dev, void* stream) {
+  if (!p || !code_dev || (!xyz_dev && n > 0) || (!out_dev && n > 0) || n < 0) return fail(DJ_ERR_INVALID, "dj_query_all: bad argument");
+  DeviceGuard g(p->device);
+  HeadCfg H{OUT_ALL20, 0, 0, 0, p->desc.slope};
+  return run_forward(p, code_dev, xyz_dev, GridSpec{}, n, H, 3, precision, out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dj_query_grid(DjPack* p, const float* code_dev, int d0, int d1, int d2, double stop, double offs,
+                             int64_t r_lo, int64_t r_hi, int use_net, int return_occ, int apply_sigmoid, int precision,
+                             float* out_dev, void* stream) {
+  if (!p || !code_dev || !out_dev) return fail(DJ_ERR_INVALID, "dj_query_grid: null argument");
+  if (d0 < 1 || d1 < 1 || d2 < 1) return fail(DJ_ERR_INVALID, "dj_query_grid: dims must be >= 1");
+  const int64_t tot = (int64_t)d0 * d1 * d2;
+  if (r_lo < 0 || r_hi > tot || r_lo > r_hi) return fail(DJ_ERR_INVALID, "dj_query_grid: row range [%lld,%lld) outside [0,%lld)", (long long)r_lo, (long long)r_hi, (long long)tot);
+  if (use_net < 0 || use_net > 3) return fail(DJ_ERR_BAD_NET, "Requested output from non-existent network: %d", use_net);
+  DeviceGuard g(p->device);
+  GridSpec G;
+  G.on = 1; G.d0 = d0; G.d1 = d1; G.d2 = d2; G.stop = stop; G.offs = offs; G.r_lo = r_lo;
+  HeadCfg H{OUT_SINGLE, use_net, return_occ, apply_sigmoid, p->desc.slope};
+  return run_forward(p, code_dev, nullptr, G, r_hi - r_lo, H, net_mask_for(use_net), precision, out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const double* pts_host, int64_t n, int use_net,
+                                      int return_occ, int apply_sigmoid, int precision, double* out_host) {
+  if (!p || !code_host || (!pts_host && n > 0) || (!out_host && n > 0) || n < 0) return fail(DJ_ERR_INVALID, "dj_decode_samples_host: bad argument");
+  if (use_net < 0 || use_net > 3) return fail(DJ_ERR_BAD_NET, "Requested output from non-existent network: %d", use_net);
+  DeviceGuard g(p->device);
+  const int64_t CH = 1 << 22;
+  const int64_t c = std::min<int64_t>(CH, std::max<int64_t>(n, 1));
+  const int nc = p->L + p->Lb;
+  // [code | pts f64 | pts f32 | out f32 | out f64]
+  const size_t o_code = 0, o_p64 = 1024, o_p32 = o_p64 + (size_t)c * 24, o_o32 = o_p32 + (size_t)c * 12,
+               o_o64 = (o_o32 + (size_t)c * 4 + 15) & ~(size_t)15;
+  DJ_CUDA(p->ws_host.reserve(o_o64 + (size_t)c * 8));
+  uint8_t* w = p->ws_host.as<uint8_t>();
+  cudaStream_t st = 0;
+  DJ_CUDA(cudaMemcpyAsync(w + o_code, code_host, nc * sizeof(float), cudaMemcpyHostToDevice, st));
+  HeadCfg H{OUT_SINGLE, use_net, return_occ, apply_sigmoid, p->desc.slope};
+  for (int64_t s = 0; s < n; s += CH) {
+    const int64_t m = std::min(CH, n - s);
+    DJ_CUDA(cudaMemcpyAsync(w + o_p64, pts_host + 3 * s, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+    simt::f64_to_f32_kernel<<<ceil_div(3 * m, 256), 256, 0, st>>>((const double*)(w + o_p64), (float*)(w + o_p32), 3 * m);
+    DJ_LAUNCHED();
+    int rc = run_forward(p, (const float*)(w + o_code), (const float*)(w + o_p32), GridSpec{}, m, H, net_mask_for(use_net),
+                         precision, (float*)(w + o_o32), st);
+    if (rc) return rc;
+    simt::f32_to_f64_kernel<<<ceil_div(m, 256), 256, 0, st>>>((const float*)(w + o_o32), (double*)(w + o_o64), m);
+    DJ_LAUNCHED();
+    DJ_CUDA(cudaMemcpyAsync(out_host + s, w + o_o64, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+  }
+  DJ_CUDA(cudaStreamSynchronize(st));
+  if (precision == DJ_PREC_BF16) return check_err_word(p, st);
+  return DJ_OK;
+}
+
+// ====================================================================== latent optimisation
+struct LatWs {
+  std::vector<float*> fH, hH;
+  float *yC, *yT, *dyC, *dyT, *G0, *G1, *colsum, *loss_acc, *grad, *terms, *bx, *bs, *bn;
+};
+
+static int carve_latent(DjPack* p, int64_t n, LatWs& W) {
+  const int nf = p->desc.f_layers - 1, nh = p->desc.h_layers - 1;
+  const size_t act = (size_t)n * 512;
+  const size_t floats = (size_t)(nf + nh + 2) * act + 4 * (size_t)n * 8 + 3 * 512 + 8 + 256 + 8 + (size_t)n * 7 + 64;
+  DJ_CUDA(p->ws_lat.reserve(floats * sizeof(float)));
+  float* q = p->ws_lat.as<float>();
+  W.fH.resize(nf + 1); W.hH.resize(nh + 1);
+  for (int l = 0; l < nf; l++) { W.fH[l] = q; q += act; }
+  for (int l = 0; l < nh; l++) { W.hH[l] = q; q += act; }
+  W.fH[nf] = nullptr; W.hH[nh] = nullptr;
+  W.G0 = q; q += act;
+  W.G1 = q; q += act;
+  W.yC = q; q += n * 8; W.yT = q; q += n * 8; W.dyC = q; q += n * 8; W.dyT = q; q += n * 8;
+  W.colsum = q; q += 3 * 512;
+  W.loss_acc = q; q += 8;
+  W.grad = q; q += 256;
+  W.terms = q; q += 8;
+  W.bx = q; q += 3 * n; W.bs = q; q += n; W.bn = q; q += 3 * n;
+  return DJ_OK;
+}
+
+// forward (activations kept) + loss + backward to dL/dcode.  Leaves grad in W.grad, terms in W.terms.
+static int latent_fwd_bwd(DjPack* p, const float* code_dev, const float* xyz, const float* sdf, const float* nrm, int64_t n,
+                          const DjLatentCfg* cfg, LatWs& W, cudaStream_t st) {
+  int rc;
+  const float slope = p->desc.slope;
+  const int H = p->H, K3 = p->K3, li = p->desc.latent_in, nlf = p->desc.f_layers, nlh = p->desc.h_layers;
+  if ((rc = launch_fold(p, code_dev, st))) return rc;
+  if ((rc = fp32_forward(p, xyz, n, 3, W.fH.data(), W.hH.data(), W.yC, W.yT, st))) return rc;
+  DJ_CUDA(cudaMemsetAsync(W.colsum, 0, (3 * 512 + 8) * sizeof(float), st));  // colsum + loss_acc are contiguous
+  simt::LossCfg LC{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, slope, 1.0f / (float)n};
+  simt::loss_grad_kernel<<<ceil_div(n, 256), 256, 0, st>>>(LC, W.yC, W.yT, 8, sdf, nrm, W.dyC, W.dyT, W.loss_acc, n);
+  DJ_LAUNCHED();
+  auto colsum = [&](const float* G, int slot) -> int {
+    dim3 grid(16, 128), block(32, 8);
+    simt::colsum_kernel<<<grid, block, 0, st>>>(G, H, n, H, W.colsum + slot * 512);
+    DJ_LAUNCHED();
+    return DJ_OK;
+  };
+  // ---- fnet: dPre_l = (dPre_{l+1} . W_{l+1}) * phi'(H_{l+1}),  H_{l+1} = output buffer of layer l
+  {
+    const float* g = W.dyC;
+    int ldg = 8, kred = 5;
+    float* pp[2] = {W.G0, W.G1};
+    int t = 0;
+    for (int l = nlf - 1; l >= 1; l--) {
+      // gradient wrt the output of layer l-1 (width f_out[l-1]); W_l is [f_out[l], f_in[l]], first f_out[l-1] columns
+      const int width = p->f_out[l - 1];
+      if ((rc = launch_sgemm<false>(g, ldg, p->fW[l], p->f_in[l], pp[t], H, n, width, kred, nullptr, 0, 0, slope, W.fH[l - 1], H, st))) return rc;
+      g = pp[t]; ldg = H; kred = width; t ^= 1;
+      if (l - 1 == li) { if ((rc = colsum(g, 1))) return rc; }
+      if (l - 1 == 0) { if ((rc = colsum(g, 0))) return rc; }
+    }
+  }
+  {
+    const float* g = W.dyT;
+    int ldg = 8, kred = 5;
+    float* pp[2] = {W.G0, W.G1};
+    int t = 0;
+    for (int l = nlh - 1; l >= 1; l--) {
+      if ((rc = launch_sgemm<false>(g, ldg, p->hW[l], p->h_in[l], pp[t], H, n, H, kred, nullptr, 0, 0, slope, W.hH[l - 1], H, st))) return rc;
+      g = pp[t]; ldg = H; kred = H; t ^= 1;
+      if (l - 1 == 0) { if ((rc = colsum(g, 2))) return rc; }
+    }
+  }
+  simt::GradFinishParams GP;
+  for (int i = 0; i < 3; i++) { GP.src[i] = p->fold.src[i]; GP.colsum[i] = W.colsum + i * 512; }
+  GP.L = p->L; GP.Lb = p->Lb;
+  GP.reg_lambda = cfg->l2reg ? cfg->code_reg_lambda : 0.f;
+  simt::grad_finish_kernel<<<p->L + p->Lb, 128, 0, st>>>(GP, code_dev, W.grad, W.loss_acc);
+  DJ_LAUNCHED();
+  simt::loss_finish_kernel<<<1, 32, 0, st>>>(W.loss_acc, W.terms);
+  DJ_LAUNCHED();
+  (void)K3;
+  return DJ_OK;
+}
+
+static int check_latent_cfg(DjPack* p, const DjLatentCfg* cfg) {
+  if (!cfg) return fail(DJ_ERR_INVALID, "null DjLatentCfg");
+  if (cfg->precision != DJ_PREC_FP32)
+    return fail(DJ_ERR_UNSUPPORTED, "latent gradient: only DJ_PREC_FP32 is implemented (tensor-core backward is not built yet)");
+  if (p->L + p->Lb > 256) return fail(DJ_ERR_UNSUPPORTED, "code length > 256");
+  return DJ_OK;
+}
+
+extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz_dev, const float* sdf_dev,
+                              const float* nrm_dev, int64_t n, const DjLatentCfg* cfg, float* grad_dev,
+                              float* loss_terms_dev, void* stream) {
+  if (!p || !code_dev || !xyz_dev || !sdf_dev || !nrm_dev || !grad_dev || n <= 0) return fail(DJ_ERR_INVALID, "dj_latent_grad: bad argument");
+  int rc;
+  if ((rc = check_latent_cfg(p, cfg))) return rc;
+  DeviceGuard g(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  LatWs W;
+  if ((rc = carve_latent(p, n, W))) return rc;
+  if ((rc = latent_fwd_bwd(p, code_dev, xyz_dev, sdf_dev, nrm_dev, n, cfg, W, st))) return rc;
+  DJ_CUDA(cudaMemcpyAsync(grad_dev, W.grad, (p->L + p->Lb) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  if (loss_terms_dev) DJ_CUDA(cudaMemcpyAsync(loss_terms_dev, W.terms, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DJ_OK;
+}
+
+extern "C" int dj_latent_optimize(DjPack* p, float* code_dev, float* adam_m_dev, float* adam_v_dev,
+                                  const float* pool_xyz_dev, const float* pool_sdf_dev, const float* pool_nrm_dev,
+                                  int64_t pool_n, const int32_t* idx_dev, const DjLatentCfg* cfg, float* log_dev,
+                                  void* stream) {
+  if (!p || !code_dev || !adam_m_dev || !adam_v_dev || !pool_xyz_dev || !pool_sdf_dev || !pool_nrm_dev || !idx_dev || pool_n <= 0)
+    return fail(DJ_ERR_INVALID, "dj_latent_optimize: bad argument");
+  int rc;
+  if ((rc = check_latent_cfg(p, cfg))) return rc;
+  if (cfg->num_iterations < 1 || cfg->num_samples < 1) return fail(DJ_ERR_INVALID, "dj_latent_optimize: iterations/samples must be >= 1");
+  DeviceGuard g(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = cfg->num_samples;
+  LatWs W;
+  if ((rc = carve_latent(p, n, W))) return rc;
+  const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
+  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations};
+  for (int e = 0; e < cfg->num_iterations; e++) {
+    simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, idx_dev + (size_t)e * n, (int)n, W.bx, W.bs, W.bn);
+    DJ_LAUNCHED();
+    if ((rc = latent_fwd_bwd(p, code_dev, W.bx, W.bs, W.bn, n, cfg, W, st))) return rc;
+    float* row = (log_dev && e % log_every == 0) ? log_dev + (size_t)(e / log_every) * 8 : nullptr;
+    simt::adam_kernel<<<1, 256, 0, st>>>(A, e, code_dev, adam_m_dev, adam_v_dev, W.grad, p->L + p->Lb, W.terms, row, p->L);
+    DJ_LAUNCHED();
+  }
+  return DJ_OK;
+}
+
+extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int num_iterations, int num_samples,
+                                  float uniform_ratio, uint64_t seed, int32_t* idx_dev, void* stream) {
+  return sampler::sample_schedule(pool_sdf_dev, pool_n, num_iterations, num_samples, uniform_ratio, seed, idx_dev, (cudaStream_t)stream);
+}
+
+// ====================================================================== marching cubes
+struct DjMcWork {
+  int device = 0;
+  mc::Dims D{};
+  DevBuf var, counts, offs, edge, misc, verts, faces;
+  int64_t nblocks = 0, nv = 0, nf = 0;
+  const float* vol = nullptr;
+  bool counted = false;
+  // create_mesh post-processing
+  double spacing[3] = {1, 1, 1}, centre = 0;
+};
+
+extern "C" int dj_mc_create(int device, DjMcWork** out) {
+  if (!out) return fail(DJ_ERR_INVALID, "dj_mc_create: null out");
+  int ndev = 0;
+  DJ_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(DJ_ERR_INVALID, "device %d out of range", device);
+  DjMcWork* w = new DjMcWork();
+  w->device = device;
+  *out = w;
+  return DJ_OK;
+}
+extern "C" int dj_mc_destroy(DjMcWork* w) {
+  if (!w) return DJ_OK;
+  DeviceGuard g(w->device);
+  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces}) b->release();
+  delete w;
+  return DJ_OK;
+}
+
+extern "C" int dj_mc_count(DjMcWork* w, const float* vol_dev, int n0, int n1, int n2, int z_off, int seam, double level,
+                           int check_range, int64_t* n_verts, int64_t* n_faces, void* stream) {
+  if (!w || !vol_dev || !n_verts || !n_faces) return fail(DJ_ERR_INVALID, "dj_mc_count: null argument");
+  if (n0 < 2 || n1 < 2 || n2 < 2) return fail(DJ_ERR_INVALID, "dj_mc_count: volume must be at least 2x2x2 (got %dx%dx%d)", n0, n1, n2);
+  DeviceGuard g(w->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  w->counted = false;
+  mc::Dims& D = w->D;
+  D.n0 = n0; D.n1 = n1; D.n2 = n2; D.z_off = z_off; D.seam = seam ? 1 : 0;
+  D.c1 = n1 - 1; D.c2 = n2 - 1;
+  D.ncells = (int64_t)(n0 - 1) * D.c1 * D.c2;
+  D.level = level;
+  w->vol = vol_dev;
+  w->nblocks = (D.ncells + mc::CB - 1) / mc::CB;
+  const int64_t nsamp = (int64_t)n0 * n1 * n2;
+  DJ_CUDA(w->var.reserve((size_t)D.ncells * sizeof(uint16_t)));
+  DJ_CUDA(w->counts.reserve((size_t)w->nblocks * sizeof(int2)));
+  DJ_CUDA(w->offs.reserve((size_t)w->nblocks * sizeof(int2)));
+  DJ_CUDA(w->misc.reserve(64));
+  long long* totals = w->misc.as<long long>();
+  int* mm = reinterpret_cast<int*>(totals + 2);
+  if (check_range) {
+    const int init[2] = {0x7FFFFFFF, (int)0x80000000};
+    DJ_CUDA(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st));
+    mc::minmax_kernel<<<1184, 256, 0, st>>>(vol_dev, nsamp, mm);
+    DJ_LAUNCHED();
+  }
+  mc::classify_kernel<<<(unsigned)w->nblocks, mc::CB, 0, st>>>(D, vol_dev, w->var.as<uint16_t>(), w->counts.as<int2>());
+  DJ_LAUNCHED();
+  mc::scan_blocks_kernel<<<1, 1024, 0, st>>>(w->counts.as<int2>(), w->nblocks, w->offs.as<int2>(), totals);
+  DJ_LAUNCHED();
+  long long h[3];
+  DJ_CUDA(cudaMemcpyAsync(h, totals, sizeof h, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaStreamSynchronize(st));
+  if (check_range) {
+    int hm[2];
+    memcpy(hm, &h[2], sizeof hm);
+    auto unord = [](int i) { int b = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &b, 4); return f; };
+    const float lo = unord(hm[0]), hi = unord(hm[1]);
+    if (level < (double)lo || level > (double)hi)
+      return fail(DJ_ERR_LEVEL_RANGE, "Surface level must be within volume data range. (level %g, range [%g, %g])", level, lo, hi);
+  }
+  w->nv = h[0];
+  w->nf = h[1];
+  if (w->nv >= 0x7FFFFFFFLL || w->nf >= 0x7FFFFFFFLL / 3) return fail(DJ_ERR_UNSUPPORTED, "mesh too large for int32 ids");
+  *n_verts = w->nv;
+  *n_faces = w->nf;
+  if (w->nf == 0 && !seam) return fail(DJ_ERR_NO_SURFACE, "No surface found at the given iso value.");
+  w->counted = true;
+  return DJ_OK;
+}
+
+extern "C" int dj_mc_fill(DjMcWork* w, int descent, float* verts_dev, int32_t* faces_dev, void* stream) {
+  if (!w || !w->counted) return fail(DJ_ERR_INVALID, "dj_mc_fill: call dj_mc_count first");
+  if ((w->nv && !verts_dev) || (w->nf && !faces_dev)) return fail(DJ_ERR_INVALID, "dj_mc_fill: null output");
+  DeviceGuard g(w->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const mc::Dims& D = w->D;
+  const int64_t nsamp = (int64_t)D.n0 * D.n1 * D.n2;
+  DJ_CUDA(w->edge.reserve((size_t)nsamp * mc::SLOTS * sizeof(int)));
+  if (D.seam) {
+    const int64_t np = (int64_t)D.n1 * D.n2;
+    mc::seam_fill_kernel<<<ceil_div(np * 2, 256), 256, 0, st>>>(w->edge.as<int>(), np);
+    DJ_LAUNCHED();
+  }
+  mc::emit_vertices_kernel<<<(unsigned)w->nblocks, mc::CB, 0, st>>>(D, w->vol, w->var.as<uint16_t>(), w->offs.as<int2>(), w->edge.as<int>(), verts_dev);
+  DJ_LAUNCHED();
+  mc::emit_faces_kernel<<<(unsigned)w->nblocks, mc::CB, 0, st>>>(D, w->var.as<uint16_t>(), w->offs.as<int2>(), w->edge.as<int>(), descent, faces_dev);
+  DJ_LAUNCHED();
+  return DJ_OK;
+}
+
+extern "C" int dj_mc_top_plane(DjMcWork* w, int32_t* ids_dev, void* stream) {
+  if (!w || !w->counted || !ids_dev) return fail(DJ_ERR_INVALID, "dj_mc_top_plane: bad argument");
+  DeviceGuard g(w->device);
+  const mc::Dims& D = w->D;
+  const int64_t np = (int64_t)D.n1 * D.n2;
+  mc::top_plane_kernel<<<ceil_div(np * 3, 256), 256, 0, (cudaStream_t)stream>>>(w->edge.as<int>() + (size_t)(D.n0 - 1) * np * mc::SLOTS, ids_dev, np);
+  DJ_LAUNCHED();
+  return DJ_OK;
+}
+
+// vertices of create_mesh: f32 index units -> f64, * spacing, swap columns 0/1, - centre
+// (core/reconstruct.py:172,179-187; float64 multiply then subtract, no fused multiply-add)
+__global__ void mesh_post_kernel(const float* __restrict__ v, double* __restrict__ out, int64_t nv, double s0, double s1,
+                                 double s2, double centre) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nv) return;
+  out[3 * i + 0] = __dsub_rn(__dmul_rn((double)v[3 * i + 1], s1), centre);
+  out[3 * i + 1] = __dsub_rn(__dmul_rn((double)v[3 * i + 0], s0), centre);
+  out[3 * i + 2] = __dsub_rn(__dmul_rn((double)v[3 * i + 2], s2), centre);
+}
+
+extern "C" int dj_create_mesh_count(DjPack* p, DjMcWork* w, const float* code_host, int d0, int d1, int d2, double padding,
+                                    int use_net, int return_occ, int apply_sigmoid, double level, int descent, int precision,
+                                    int64_t* n_verts, int64_t* n_faces) {
+  if (!p || !w || !code_host || !n_verts || !n_faces) return fail(DJ_ERR_INVALID, "dj_create_mesh_count: null argument");
+  if (p->device != w->device) return fail(DJ_ERR_INVALID, "pack and marching-cubes workspace live on different devices");
+  DeviceGuard g(p->device);
+  cudaStream_t st = 0;
+  const int64_t tot = (int64_t)d0 * d1 * d2;
+  const int nc = p->L + p->Lb;
+  DJ_CUDA(p->ws_vol.reserve((size_t)tot * sizeof(float) + 1024));
+  float* code_dev = p->ws_vol.as<float>();
+  float* vol = code_dev + 256;
+  DJ_CUDA(cudaMemcpyAsync(code_dev, code_host, nc * sizeof(float), cudaMemcpyHostToDevice, st));
+  const double stop = 1.0 + (padding * 2), offs = 0.5 + padding;
+  int rc = dj_query_grid(p, code_dev, d0, d1, d2, stop, offs, 0, tot, use_net, return_occ, apply_sigmoid, precision, vol, st);
+  if (rc) return rc;
+  // values.reshape(dims): the flat rows are reinterpreted as a C-contiguous [d0, d1, d2] volume (core/reconstruct.py:162)
+  rc = dj_mc_count(w, vol, d0, d1, d2, 0, 0, level, 1, n_verts, n_faces, st);
+  if (precision == DJ_PREC_BF16) {
+    int rc2 = check_err_word(p, st);
+    if (rc2) return rc2;
+  }
+  if (rc) return rc;
+  DJ_CUDA(w->verts.reserve((size_t)w->nv * 3 * (sizeof(float) + sizeof(double)) + 16));
+  DJ_CUDA(w->faces.reserve((size_t)w->nf * 3 * sizeof(int)));
+  rc = dj_mc_fill(w, descent, w->verts.as<float>(), w->faces.as<int>(), st);
+  if (rc) return rc;
+  w->spacing[0] = (1 + (padding * 2)) / d0;
+  w->spacing[1] = (1 + (padding * 2)) / d1;
+  w->spacing[2] = (1 + (padding * 2)) / d2;
+  w->centre = 0.5 + padding;
+  return DJ_OK;
+}
+
+extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* faces_host) {
+  if (!w || !w->counted || !verts_host || !faces_host) return fail(DJ_ERR_INVALID, "dj_create_mesh_fetch: bad argument");
+  DeviceGuard g(w->device);
+  cudaStream_t st = 0;
+  double* v64 = reinterpret_cast<double*>(w->verts.as<float>() + (((size_t)w->nv * 3 + 1) & ~(size_t)1));
+  mesh_post_kernel<<<ceil_div(w->nv, 256), 256, 0, st>>>(w->verts.as<float>(), v64, w->nv, w->spacing[0], w->spacing[1], w->spacing[2], w->centre);
+  DJ_LAUNCHED();
+  DJ_CUDA(cudaMemcpyAsync(verts_host, v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaMemcpyAsync(faces_host, w->faces.as<int>(), (size_t)w->nf * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaStreamSynchronize(st));
+  return DJ_OK;
+}

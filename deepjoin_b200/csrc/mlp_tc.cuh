@@ -1,0 +1,352 @@
+// Fused persistent decoder forward on tcgen05 tensor cores (sm_100a).
+//
+// replaces: Decoder.forward  (networks/decoder_z_lb_both_leaky_n_sdf.py:174-457) for one latent
+// code shared by all rows, i.e. what decode_samples (core/reconstruct.py:115-129) feeds it.
+//
+// One CTA owns a tile of 128 query points and walks BOTH MLPs (fnet then hnet) without the
+// activations ever leaving the SM:
+//   * the latent columns of lin0 / lin4 / hnet_lin0 are folded into per-shape constants by
+//     fold_kernel (mlp_simt.cuh); the remaining K=3 xyz products run on CUDA cores;
+//   * every 512-wide layer is a 128 x N x K bf16 GEMM: A = activations in shared memory
+//     (K-major, 128-byte swizzle, written by the epilogue), B = weight tiles streamed from L2 by
+//     the TMA engine (cp.async.bulk, 16 KB pre-swizzled stages, mbarrier ring), D = fp32
+//     accumulators in TMEM (4 x 128 columns = all 512 columns);
+//   * epilogue warps drain TMEM 64 columns at a time: + bias, LeakyReLU, -> bf16 -> the A operand
+//     of the next layer, releasing each 64-wide K chunk through an mbarrier so the next layer's
+//     MMAs start while the drain is still running;
+//   * heads (tanh / sigmoid / B,R combine) in the last epilogue; 4 B per point leave the SM.
+//
+// Warp roles (192 threads): warp 0 = weight producer, warp 1 = MMA issuer (one thread) + TMEM
+// allocation, warps 2..5 = epilogue (one TMEM lane quarter each, one point per thread).
+#pragma once
+#include "common.cuh"
+#include "ptx.cuh"
+#include "heads.cuh"
+
+namespace dj {
+namespace tc {
+
+constexpr int TILE_M = 128;
+constexpr int KCH = 64;                       // k-chunk: 64 bf16 = one 128 B swizzle row
+constexpr int NCH = 128;                      // accumulator chunk (TMEM columns)
+constexpr int A_CHUNK_BYTES = TILE_M * KCH * 2;  // 16 KB
+constexpr int STAGE_BYTES = NCH * KCH * 2;       // 16 KB
+constexpr int NSTAGES = 5;
+constexpr int MAX_LAYERS = 10;
+constexpr int NTHREADS = 192;
+
+constexpr int SM_A = 0;
+constexpr int SM_W = SM_A + 8 * A_CHUNK_BYTES;           // 131072
+constexpr int SM_BIAS = SM_W + NSTAGES * STAGE_BYTES;    // + 81920
+constexpr int SM_TAB = SM_BIAS + 2 * 512 * 4;            // + 4096
+constexpr int SM_BAR = SM_TAB + 512 * 16;                // + 8192
+constexpr int SM_END = SM_BAR + 256;
+constexpr int SMEM_BYTES = SM_END + 1024;                // slack for 1024-B alignment
+
+enum { KIND_HIDDEN = 0, KIND_HIDDEN_XYZ = 1, KIND_HEAD = 2 };
+
+struct TcLayer {
+  int16_t n_chunks;   // accumulator chunks of this layer
+  int16_t k_chunks;   // 64-wide chunks of the input
+  int16_t mma_n;      // N of each MMA (128 hidden, 16 head)
+  int16_t kind;
+  int32_t bias_off;   // float offset into TcParams::bias (KIND_HIDDEN / KIND_HEAD)
+  int32_t table;      // xyzw table id (KIND_HIDDEN_XYZ)
+  int32_t stage_bytes;
+  int32_t pad;
+};
+struct TcNet {
+  int32_t n_layers;
+  int32_t l0_table;
+  int32_t head_leaky;
+  int32_t pad;
+  const uint8_t* stream;
+  TcLayer layers[MAX_LAYERS];
+};
+struct TcParams {
+  TcNet nets[2];
+  int32_t net_mask;
+  int32_t grid_mode;
+  const float* bias;
+  const float4* tables;  // [3][512] (wx, wy, wz, c) per-shape constants
+  const float* xyz;
+  int64_t n;
+  // grid mode: r = (i*d0 + j)*d2 + k -> (lin0[j], lin1[i], lin2[k])
+  int32_t d0, d1, d2, pad0;
+  double step0, step1, step2, stop, offs;
+  int64_t r_lo;
+  HeadCfg head;
+  float* out;
+  unsigned int* err;
+};
+
+__device__ __forceinline__ float lin_axis(int t, int d, double step, double stop, double offs) {
+  // np.linspace(0, stop, d)[t] - offs in float64, no fused multiply-add, then f32
+  double v = (t == d - 1) ? stop : __dmul_rn((double)t, step);
+  return (float)__dsub_rn(v, offs);
+}
+
+__device__ __forceinline__ void grid_point(const TcParams& P, int64_t r, float& x, float& y, float& z) {
+  int k = (int)(r % P.d2);
+  int64_t q = r / P.d2;
+  int j = (int)(q % P.d0);
+  int i = (int)(q / P.d0);
+  x = lin_axis(j, P.d0, P.step0, P.stop, P.offs);
+  y = lin_axis(i, P.d1, P.step1, P.stop, P.offs);
+  z = lin_axis(k, P.d2, P.step2, P.stop, P.offs);
+}
+
+__device__ __forceinline__ float leaky(float v, float slope) { return fmaxf(v, v * slope); }
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_constant__ TcParams P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t sA = base + SM_A, sW = base + SM_W;
+  float* sBias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float4* sTab = reinterpret_cast<float4*>(smem + SM_TAB);
+  const uint32_t bar0 = base + SM_BAR;
+  auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGES + s); };
+  auto A_READY = [&](int c) { return bar0 + 8u * (2 * NSTAGES + c); };
+  auto ACC_FULL = [&](int j) { return bar0 + 8u * (2 * NSTAGES + 8 + j); };
+  auto ACC_EMPTY = [&](int j) { return bar0 + 8u * (2 * NSTAGES + 12 + j); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 16));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGES; s++) {
+      ptx::mbar_init(W_FULL(s), 1);
+      ptx::mbar_init(W_EMPTY(s), 1);
+    }
+    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(c), 128);
+    for (int j = 0; j < 4; j++) {
+      ptx::mbar_init(ACC_FULL(j), 1);
+      ptx::mbar_init(ACC_EMPTY(j), 128);
+    }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(ptx::smem_u32((const void*)tmem_slot), 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer (TMA engine, 1-D bulk copies) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int net = 0; net < 2; net++) {
+          if (!((P.net_mask >> net) & 1)) continue;
+          const TcNet& N = P.nets[net];
+          const uint8_t* src = N.stream;
+          for (int l = 0; l < N.n_layers; l++) {
+            const int ns = N.layers[l].n_chunks * N.layers[l].k_chunks;
+            const uint32_t bytes = (uint32_t)N.layers[l].stage_bytes;
+            for (int s = 0; s < ns; s++) {
+              ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage);
+              ptx::mbar_expect_tx(W_FULL(stage), bytes);
+              ptx::bulk_g2s(sW + stage * STAGE_BYTES, src, bytes, W_FULL(stage));
+              src += bytes;
+              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (single thread) =====================
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, a_ph = 0, e_ph = 0;
+      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        for (int net = 0; net < 2; net++) {
+          if (!((P.net_mask >> net) & 1)) continue;
+          const TcNet& N = P.nets[net];
+          for (int l = 0; l < N.n_layers; l++) {
+            const TcLayer L = N.layers[l];
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)L.mma_n);
+            for (int j = 0; j < L.n_chunks; j++) {
+              ptx::mbar_wait(ACC_EMPTY(j), ((e_ph >> j) & 1) ^ 1, P.err, 0x200 | j);
+              e_ph ^= 1u << j;
+              ptx::tc_fence_after();
+              const uint32_t d_tmem = tmem_base + (uint32_t)(j * NCH);
+              for (int c = 0; c < L.k_chunks; c++) {
+                if (j == 0) {
+                  ptx::mbar_wait(A_READY(c), (a_ph >> c) & 1, P.err, 0x300 | c);
+                  a_ph ^= 1u << c;
+                }
+                ptx::mbar_wait(W_FULL(stage), phase, P.err, 0x400 | stage);
+                ptx::tc_fence_after();
+                const uint32_t a_addr = sA + c * A_CHUNK_BYTES;
+                const uint32_t b_addr = sW + stage * STAGE_BYTES;
+#pragma unroll
+                for (int k = 0; k < KCH / 16; k++) {
+                  ptx::mma_f16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * 32),
+                                  ptx::umma_desc_sw128_kmajor(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
+                }
+                ptx::mma_commit(W_EMPTY(stage));
+                if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+              }
+              ptx::mma_commit(ACC_FULL(j));
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: one point per thread =====================
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_row = sA + row * 128;
+    const int sw = row & 7;
+    const float slope = P.head.slope;
+    uint32_t f_ph = 0;
+    int bias_buf = 0;
+
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int64_t g = tile * TILE_M + row;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (g < P.n) {
+        if (P.grid_mode) grid_point(P, P.r_lo + g, x, y, z);
+        else { x = __ldg(P.xyz + 3 * g); y = __ldg(P.xyz + 3 * g + 1); z = __ldg(P.xyz + 3 * g + 2); }
+      }
+      float yc[5] = {0, 0, 0, 0, 0}, yt[5] = {0, 0, 0, 0, 0};
+
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const TcNet& N = P.nets[net];
+        // ---- layer 0 on CUDA cores: K = 3 after folding the latent into table.w
+        epi_bar();  // everybody is past the previous use of sTab / sBias
+        {
+          const float4* t = P.tables + N.l0_table * 512;
+#pragma unroll
+          for (int i = 0; i < 4; i++) sTab[et + 128 * i] = __ldg(t + et + 128 * i);
+          if (N.layers[0].kind == KIND_HIDDEN) {
+            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + N.layers[0].bias_off) + et);
+            reinterpret_cast<float4*>(sBias + bias_buf * 512)[et] = b;
+          }
+        }
+        epi_bar();
+#pragma unroll 1
+        for (int c = 0; c < 8; c++) {
+#pragma unroll
+          for (int gq = 0; gq < 8; gq++) {
+            float v[8];
+#pragma unroll
+            for (int f = 0; f < 8; f++) {
+              const float4 t = sTab[c * 64 + gq * 8 + f];
+              v[f] = leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
+            }
+            const uint32_t dst = a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ptx::pack_bf16x2(v[0], v[1])),
+                         "r"(ptx::pack_bf16x2(v[2], v[3])), "r"(ptx::pack_bf16x2(v[4], v[5])),
+                         "r"(ptx::pack_bf16x2(v[6], v[7]))
+                         : "memory");
+          }
+          ptx::fence_proxy_async_smem();
+          ptx::mbar_arrive(A_READY(c));
+        }
+
+        for (int l = 0; l < N.n_layers; l++) {
+          const TcLayer L = N.layers[l];
+          const int last = L.n_chunks - 1;
+          ptx::mbar_wait(ACC_FULL(last), (f_ph >> last) & 1, P.err, 0x500 | l);
+          ptx::tc_fence_after();
+          if (L.kind == KIND_HEAD) {
+            f_ph ^= 1u;
+            uint32_t r[8];
+            ptx::tmem_ld8(tmem_lane, r);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(ACC_EMPTY(0));
+            float* dst = net == 0 ? yc : yt;
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+              float v = __uint_as_float(r[i]) + __ldg(P.bias + L.bias_off + i);
+              dst[i] = N.head_leaky ? leaky(v, slope) : v;
+            }
+            continue;
+          }
+          epi_bar();  // all epilogue warps finished the previous drain: smem tables may be rewritten
+          // prefetch what the NEXT layer's drain needs
+          const bool has_next = (l + 1 < N.n_layers);
+          const int next_kind = has_next ? N.layers[l + 1].kind : -1;
+          float4 pre_b = make_float4(0, 0, 0, 0), pre_t[4];
+          if (next_kind == KIND_HIDDEN) {
+            pre_b = __ldg(reinterpret_cast<const float4*>(P.bias + N.layers[l + 1].bias_off) + et);
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            const float4* t = P.tables + N.layers[l + 1].table * 512;
+#pragma unroll
+            for (int i = 0; i < 4; i++) pre_t[i] = __ldg(t + et + 128 * i);
+          }
+          const float* bias = sBias + bias_buf * 512;
+          for (int j = 0; j <= last; j++) {
+            if (j != last) ptx::mbar_wait(ACC_FULL(j), (f_ph >> j) & 1, P.err, 0x600 | j);
+            f_ph ^= 1u << j;
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+              const int col0 = j * NCH + half * 64;
+              uint32_t r0[32], r1[32];
+              ptx::tmem_ld32(tmem_lane + col0, r0);
+              ptx::tmem_ld32(tmem_lane + col0 + 32, r1);
+              ptx::tmem_wait_ld();
+              if (half == 1) {
+                ptx::tc_fence_before();
+                ptx::mbar_arrive(ACC_EMPTY(j));
+              }
+              const int c = 2 * j + half;
+#pragma unroll
+              for (int gq = 0; gq < 8; gq++) {
+                float v[8];
+#pragma unroll
+                for (int f = 0; f < 8; f++) {
+                  const int i = gq * 8 + f;
+                  const float acc = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
+                  if (L.kind == KIND_HIDDEN_XYZ) {
+                    const float4 t = sTab[col0 + i];
+                    v[f] = leaky(acc + fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
+                  } else {
+                    v[f] = leaky(acc + bias[col0 + i], slope);
+                  }
+                }
+                const uint32_t dst = a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4);
+                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ptx::pack_bf16x2(v[0], v[1])),
+                             "r"(ptx::pack_bf16x2(v[2], v[3])), "r"(ptx::pack_bf16x2(v[4], v[5])),
+                             "r"(ptx::pack_bf16x2(v[6], v[7]))
+                             : "memory");
+              }
+              ptx::fence_proxy_async_smem();
+              ptx::mbar_arrive(A_READY(c));
+            }
+          }
+          // publish the prefetched tables for the next drain (made visible by its epi_bar)
+          if (next_kind == KIND_HIDDEN) {
+            bias_buf ^= 1;
+            reinterpret_cast<float4*>(sBias + bias_buf * 512)[et] = pre_b;
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) sTab[et + 128 * i] = pre_t[i];
+          }
+        }
+      }
+      if (g < P.n) write_heads(P.head, yc, yt, P.out, g);
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace tc
+}  // namespace dj

@@ -1,0 +1,121 @@
+"""Drop-in for the function ``reconstruct()`` of the reference's ``reconstruct.py:19-226``
+(duplicated in ``reconstruct_single.py:19-226``): per-shape Adam optimisation of
+[latent (L), break_latent (Lb)] through the frozen decoder.
+
+Same arguments, same return value ``(loss_dict, code[1, L+Lb])``, same initialisation
+(``torch.ones(1,L).normal_(0, stat)`` on the CPU generator, :48-50) and the same mini-batch
+stream (numpy global RNG consumed exactly like core/data.py does), but the 800-iteration loop
+-- batch gather, forward, clamped-L1 + BCE + normal loss, backward to the code only, Adam, lr
+step, loss logging every 10th iteration -- runs on the device without host round trips
+(dj_latent_optimize).  ``sampling_method="device"`` (extension) also draws the schedule on the
+device (dj_sample_schedule), removing the reference's ~60 ms/iteration of host sampling."""
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+from deepjoin_b200 import _lib
+from deepjoin_b200.core import data as _data
+
+LOG_KEYS = ("epoch", "loss", "sdf_data_loss", "occ_data_loss", "norm_loss", "reg_loss", "mag", "h_mag")
+
+
+def make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio=0.2):
+    """Row indices of every iteration's mini-batch, consuming numpy's global RNG exactly as the
+    reference loop does (reconstruct.py:114-118 -> core/data.py:15-73)."""
+    sched = np.empty((num_iterations, num_samples), dtype=np.int32)
+    vals = np.asarray(b_sdf_gt).reshape(-1)
+    for e in range(num_iterations):
+        sched[e] = _data.select_sample_indices(vals, num_samples, uniform_ratio=uniform_ratio)
+    return sched
+
+
+def init_code(latent_size, break_latent_size, stat):
+    """reconstruct.py:48-53 (CPU generator, so torch.manual_seed reproduces the reference)."""
+    if type(stat) == type(0.1):
+        latent = torch.ones(1, latent_size).normal_(mean=0, std=stat)
+        break_latent = torch.ones(1, break_latent_size).normal_(mean=0, std=stat)
+    else:
+        latent = torch.normal(stat[0].detach(), stat[1].detach())
+        break_latent = torch.normal(stat[0].detach(), stat[1].detach())
+    return torch.cat([latent.reshape(1, -1), break_latent.reshape(1, -1)], dim=1).float()
+
+
+def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, lambda1, lambda3, clamp_dist,
+                  l2reg=True, code_reg_lambda=1e-4, log_every=10, precision="fp32"):
+    """Device loop.  pool_* CUDA f32 tensors ([M,3], [M], [M,3]); schedule CUDA int32
+    [iterations, num_samples].  Returns (log [ceil(it/log_every), 8] CUDA, code [1, L+Lb] CUDA)."""
+    dev = pool_xyz.device
+    pack = decoder.pack(dev)
+    iters, ns = int(schedule.shape[0]), int(schedule.shape[1])
+    cfg = _lib.LatentCfg(iters, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
+                         float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, int(log_every),
+                         _lib.PREC[precision])
+    code = code0.detach().reshape(-1).to(device=dev, dtype=torch.float32).clone().contiguous()
+    m = torch.zeros_like(code)
+    v = torch.zeros_like(code)
+    log = torch.zeros(((iters + log_every - 1) // log_every, 8), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dj_latent_optimize(
+            pack.handle, code.data_ptr(), m.data_ptr(), v.data_ptr(), pool_xyz.data_ptr(), pool_sdf.data_ptr(),
+            pool_nrm.data_ptr(), pool_xyz.shape[0], schedule.data_ptr(), _lib.ctypes.byref(cfg), log.data_ptr(),
+            _lib.stream_ptr()))
+    return log, code.reshape(1, -1)
+
+
+def latent_grad(decoder, code, xyz, sdf, nrm, lambda1=1.0, lambda3=1.0, clamp_dist=0.1, l2reg=True,
+                code_reg_lambda=1e-4, precision="fp32"):
+    """One forward+backward: (dL/dcode [L+Lb], loss terms [5] = loss, sdf, occ, norm, reg)."""
+    dev = xyz.device
+    pack = decoder.pack(dev)
+    cfg = _lib.LatentCfg(1, int(xyz.shape[0]), 0.0, float(lambda1), float(lambda3), float(clamp_dist),
+                         float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, 10, _lib.PREC[precision])
+    code = code.detach().reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+    grad = torch.empty_like(code)
+    terms = torch.empty(5, device=dev, dtype=torch.float32)
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    xyz, sdf, nrm = f32(xyz), f32(sdf).reshape(-1), f32(nrm)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dj_latent_grad(pack.handle, code.data_ptr(), xyz.data_ptr(), sdf.data_ptr(),
+                                             nrm.data_ptr(), xyz.shape[0], _lib.ctypes.byref(cfg), grad.data_ptr(),
+                                             terms.data_ptr(), _lib.stream_ptr()))
+    return grad, terms
+
+
+def reconstruct(decoder, num_iterations, latent_size, break_latent_size, test_sdf, stat, lambda1, lambda2, lambda3,
+                clamp_dist, sampling_method=None, num_samples=30000, lr=5e-4, l2reg=False, code_reg_lambda=1e-4,
+                iter_path=None, loss_version=None):
+    decoder.eval()
+    if sampling_method == "surface_interior_only":
+        raise NotImplementedError("sampling_method='surface_interior_only' (partial-view baseline path)")
+    dev = next(decoder.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("deepjoin_b200: the decoder must live on a CUDA device")
+    if latent_size != decoder.latent_size or break_latent_size != decoder.tool_latent_size:
+        raise ValueError("latent sizes do not match the decoder")
+    code0 = init_code(latent_size, break_latent_size, stat)
+
+    pts_gt, b_sdf_gt, b_n_gt = test_sdf
+    pool_xyz = torch.from_numpy(np.ascontiguousarray(pts_gt, dtype=np.float32)).to(dev)
+    pool_sdf = torch.from_numpy(np.ascontiguousarray(np.asarray(b_sdf_gt).reshape(-1), dtype=np.float32)).to(dev)
+    pool_nrm = torch.from_numpy(np.ascontiguousarray(b_n_gt, dtype=np.float32)).to(dev)
+
+    if sampling_method == "device":
+        sched = torch.empty((num_iterations, num_samples), device=dev, dtype=torch.int32)
+        seed = int(np.random.randint(0, 2 ** 31 - 1))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().dj_sample_schedule(pool_sdf.data_ptr(), pool_sdf.shape[0], int(num_iterations),
+                                                     int(num_samples), 0.2, seed, sched.data_ptr(), _lib.stream_ptr()))
+    else:
+        sched = torch.from_numpy(make_schedule(b_sdf_gt, num_iterations, num_samples, 0.2)).to(dev)
+
+    log, code = optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, sched, lr, lambda1, lambda3, clamp_dist,
+                              l2reg=l2reg, code_reg_lambda=code_reg_lambda, log_every=10,
+                              precision=getattr(decoder, "latent_precision", "fp32"))
+    log = log.cpu().numpy()
+    loss_dict = defaultdict(lambda: [])
+    for row in log:
+        loss_dict["epoch"].append(int(row[0]))
+        for k, val in zip(LOG_KEYS[1:], row[1:]):
+            loss_dict[k].append(float(val))
+    return dict(loss_dict), code
