@@ -75,7 +75,10 @@ def decode_shape_device(vec, decoder, dims, use_net=1, padding=0.0, sigmoid=True
     d0, d1, d2 = [int(d) for d in dims]
     total = d0 * d1 * d2
     r_lo, r_hi = (0, total) if rows is None else rows
-    code = torch.from_numpy(_code_host(vec)).to(dev)
+    if isinstance(vec, torch.Tensor) and vec.device == dev:
+        code = vec.detach().reshape(-1).to(torch.float32).contiguous()  # stays on the device: no sync
+    else:
+        code = torch.from_numpy(_code_host(vec)).to(dev)
     out = torch.empty(r_hi - r_lo, device=dev, dtype=torch.float32)
     with torch.cuda.device(dev):
         _lib.check(_lib.lib().dj_query_grid(

@@ -5,6 +5,7 @@
 #include "mlp_tc.cuh"
 #include "mc.cuh"
 #include "sampler.cuh"
+#include "debug_probe.cuh"
 
 using namespace dj;
 
@@ -709,5 +710,44 @@ extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* fa
   DJ_CUDA(cudaMemcpyAsync(verts_host, v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaMemcpyAsync(faces_host, w->faces.as<int>(), (size_t)w->nf * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaStreamSynchronize(st));
+  return DJ_OK;
+}
+
+// ====================================================================== debug probe (not product path)
+// A_host [128,K], W_host [128,K] fp32 (nn.Linear layout); D_host [128,128] = bf16(A) . bf16(W)^T.
+// desc_tmpl == 0 / k_adv_bytes == 0 / idesc == 0 select the encodings the product kernel uses.
+extern "C" int dj_debug_umma_probe(const float* A_host, const float* W_host, int K, int use_bulk, int k_adv_bytes,
+                                   uint32_t idesc, uint64_t desc_tmpl, float* D_host) {
+  if (!A_host || !W_host || !D_host || K < 64 || K > 256 || K % 64) return fail(DJ_ERR_INVALID, "dj_debug_umma_probe: bad argument");
+  float *A = nullptr, *D = nullptr;
+  uint8_t* B = nullptr;
+  unsigned int* err = nullptr;
+  std::vector<uint8_t> blob((size_t)(K / 64) * 16384);
+  for (int c = 0; c < K / 64; c++) pack_tile(W_host, K, 128, K, 0, c * 64, 128, blob.data() + (size_t)c * 16384);
+  DJ_CUDA(cudaMalloc((void**)&A, 128 * K * sizeof(float)));
+  DJ_CUDA(cudaMalloc((void**)&D, 128 * 128 * sizeof(float)));
+  DJ_CUDA(cudaMalloc((void**)&B, blob.size()));
+  DJ_CUDA(cudaMalloc((void**)&err, 4));
+  DJ_CUDA(cudaMemset(err, 0, 4));
+  DJ_CUDA(cudaMemset(D, 0xff, 128 * 128 * sizeof(float)));
+  DJ_CUDA(cudaMemcpy(A, A_host, 128 * K * sizeof(float), cudaMemcpyHostToDevice));
+  DJ_CUDA(cudaMemcpy(B, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+  probe::ProbeParams P;
+  P.A = A; P.Bblob = B; P.D = D; P.K = K; P.use_bulk = use_bulk;
+  P.k_adv_bytes = k_adv_bytes ? k_adv_bytes : 32;
+  P.idesc = idesc ? idesc : ptx::umma_idesc_bf16(128, 128);
+  P.desc_tmpl = desc_tmpl ? desc_tmpl : (((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61));
+  P.err = err;
+  const int smem = 8 * 16384 + 1024 + 64;
+  DJ_CUDA(cudaFuncSetAttribute(probe::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  probe::umma_probe_kernel<<<1, 128, smem>>>(P);
+  DJ_LAUNCHED();
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned int h = 0;
+  if (e == cudaSuccess) cudaMemcpy(&h, err, 4, cudaMemcpyDeviceToHost);
+  if (e == cudaSuccess) e = cudaMemcpy(D_host, D, 128 * 128 * sizeof(float), cudaMemcpyDeviceToHost);
+  cudaFree(A); cudaFree(D); cudaFree(B); cudaFree(err);
+  if (e != cudaSuccess) return fail(DJ_ERR_CUDA, "umma probe: %s (err word 0x%08x)", cudaGetErrorString(e), h);
+  if (h) return fail(DJ_ERR_DEVICE, "umma probe watchdog 0x%08x", h);
   return DJ_OK;
 }

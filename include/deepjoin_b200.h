@@ -175,6 +175,12 @@ int dj_create_mesh_count(DjPack* pack, DjMcWork* work, const float* code_host, i
                          int descent, int precision, int64_t* n_verts, int64_t* n_faces);
 int dj_create_mesh_fetch(DjMcWork* work, double* verts_host, int32_t* faces_host);
 
+/* DEBUG ONLY (tools/gpu_diag.py): one 128x128xK bf16 UMMA built from the product kernel's pieces;
+ * D_host [128,128] = bf16(A_host [128,K]) . bf16(W_host [128,K])^T.  Zero for k_adv_bytes / idesc /
+ * desc_tmpl selects the product encodings. */
+int dj_debug_umma_probe(const float* A_host, const float* W_host, int K, int use_bulk, int k_adv_bytes,
+                        uint32_t idesc, uint64_t desc_tmpl, float* D_host);
+
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t dj_launch_count(int reset);
 

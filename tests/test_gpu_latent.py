@@ -1,0 +1,134 @@
+"""GPU parity of the latent-code optimisation (fused loss + backward-to-code + Adam on the device)
+against autograd through the oracle and against the reference's own reconstruct() run (golden)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import decoder_oracle as O
+from oracle import synth
+from tests import util
+
+pytestmark = pytest.mark.gpu
+G = util.GOLDEN
+
+
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+def test_latent_gradient_vs_reference_autograd(kind):
+    from deepjoin_b200 import reconstruct as R
+    g = np.load(os.path.join(G, "reconstruct.npz"))
+    dec = util.make_decoder(0, kind, precision="fp32")
+    bp, bs = g[kind + "_batch_pts"], g[kind + "_batch_sdf"]
+    code0 = torch.from_numpy(g[kind + "_code0"])
+    grad, terms = R.latent_grad(dec, code0.cuda(), torch.from_numpy(bp[0][:, :3]).cuda(),
+                                torch.from_numpy(bs[0]).cuda(), torch.from_numpy(bp[0][:, 3:]).cuda())
+    ref = g[kind + "_grad0"].reshape(-1)
+    got = grad.cpu().numpy()
+    assert abs(float(terms[0]) - float(g[kind + "_loss0"])) < 2e-5
+    assert np.abs(got - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7, np.abs(got - ref).max() / np.abs(ref).max()
+    # terms add up and match the oracle term by term
+    net = util.oracle_net(0, kind)
+    _, t = O.latent_grad(net, code0, torch.from_numpy(bp[0][:, :3]), torch.from_numpy(bs[0]), torch.from_numpy(bp[0][:, 3:]))
+    assert np.allclose(terms.cpu().numpy(), np.asarray(t), atol=2e-5)
+
+
+def test_latent_gradient_options():
+    """lambda1 = 0 / lambda3 = 0 / no regulariser / other clamp: each switch against the oracle."""
+    from deepjoin_b200 import reconstruct as R
+    dec = util.make_decoder(1, "trained_norm", precision="fp32")
+    net = util.oracle_net(1, "trained_norm")
+    xyz, sdf, nrm = synth.make_sample_set(4000, seed=1)
+    idx = np.random.default_rng(0).permutation(4000)[:777]
+    x = torch.from_numpy(xyz[idx].astype(np.float32))
+    s = torch.from_numpy(sdf[idx].astype(np.float32))
+    n = torch.from_numpy(nrm[idx].astype(np.float32))
+    code = util.trained_code(1)
+    for kw in (dict(lambda1=0.0), dict(lambda3=0.0), dict(l2reg=False), dict(clamp_dist=0.03), dict(lambda1=0.5, lambda3=2.0)):
+        ref, t = O.latent_grad(net, code, x, s, n, **kw)
+        grad, terms = R.latent_grad(dec, code.cuda(), x.cuda(), s.cuda(), n.cuda(), **kw)
+        ref = ref.numpy()
+        assert np.abs(grad.cpu().numpy() - ref).max() <= 3e-3 * np.abs(ref).max() + 1e-7, kw
+        assert np.allclose(terms.cpu().numpy(), np.asarray(t), atol=5e-5), kw
+
+
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+def test_adam_loop_vs_reference_reconstruct(kind):
+    """The device loop fed the batches the reference's own run drew reproduces its loss log and code."""
+    from deepjoin_b200 import reconstruct as R
+    g = np.load(os.path.join(G, "reconstruct.npz"))
+    dec = util.make_decoder(0, kind, precision="fp32")
+    bp, bs = g[kind + "_batch_pts"], g[kind + "_batch_sdf"]
+    iters, ns = bp.shape[0], bp.shape[1]
+    pool_xyz = torch.from_numpy(bp[:, :, :3].reshape(-1, 3).copy()).cuda()
+    pool_nrm = torch.from_numpy(bp[:, :, 3:].reshape(-1, 3).copy()).cuda()
+    pool_sdf = torch.from_numpy(bs.reshape(-1).copy()).cuda()
+    sched = torch.arange(iters * ns, dtype=torch.int32).reshape(iters, ns).cuda()
+    log, code = R.optimize_code(dec, torch.from_numpy(g[kind + "_code0"]), pool_xyz, pool_sdf, pool_nrm, sched,
+                                lr=5e-3, lambda1=1.0, lambda3=1.0, clamp_dist=0.1, l2reg=True, code_reg_lambda=1e-4)
+    log = log.cpu().numpy()
+    assert log.shape == (1, 8) and log[0, 0] == 0
+    assert abs(log[0, 1] - g[kind + "_log_loss"][0]) < 2e-5
+    assert abs(log[0, 6] - g[kind + "_log_mag"][0]) < 1e-5 and abs(log[0, 7] - g[kind + "_log_h_mag"][0]) < 1e-5
+    assert np.abs(code.cpu().numpy() - g[kind + "_code"]).max() < 2e-3
+
+
+def test_reconstruct_dropin_seeded_like_the_reference():
+    """reconstruct(): same seeds -> same initial code and the same mini-batches as the reference run."""
+    from deepjoin_b200.reconstruct import reconstruct
+    g = np.load(os.path.join(G, "reconstruct.npz"))
+    dec = util.make_decoder(0, "default", precision="fp32")
+    xyz, sdf, nrm = synth.make_sample_set(4000, seed=3)
+    np.random.seed(5)
+    torch.manual_seed(5)
+    loss, code = reconstruct(dec, 6, 128, 64, [xyz, sdf, nrm], 0.01, 1.0, 0.0, 1.0, 0.1, num_samples=512, lr=5e-3,
+                             l2reg=True, code_reg_lambda=1e-4)
+    assert set(loss) == {"epoch", "loss", "sdf_data_loss", "occ_data_loss", "norm_loss", "reg_loss", "mag", "h_mag"}
+    assert loss["epoch"] == [0]
+    assert abs(loss["loss"][0] - g["default_log_loss"][0]) < 2e-5
+    assert tuple(code.shape) == (1, 192) and code.is_cuda
+    assert np.abs(code.cpu().numpy() - g["default_code"]).max() < 2e-3
+
+
+def test_longer_run_decreases_loss_and_logs_every_10():
+    from deepjoin_b200.reconstruct import reconstruct
+    dec = util.make_decoder(0, "trained_norm", precision="fp32")
+    xyz, sdf, nrm = synth.make_sample_set(20000, seed=2)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    loss, code = reconstruct(dec, 60, 128, 64, [xyz, sdf, nrm], 0.01, 1.0, 0.0, 1.0, 0.1, num_samples=2000, lr=5e-3,
+                             l2reg=True)
+    assert loss["epoch"] == [0, 10, 20, 30, 40, 50]
+    assert loss["loss"][-1] < loss["loss"][0]
+    assert torch.isfinite(code).all()
+
+
+def test_device_sampler_semantics():
+    """dj_sample_schedule: class balance, [pos..., neg...] order, no duplicates inside a class window,
+    surface rows + 1/4 of the uniform rows, NoSamplesError on an empty class."""
+    from deepjoin_b200 import _lib
+    from deepjoin_b200.core import errors
+    xyz, sdf, nrm = synth.make_sample_set(40000, seed=0)
+    s = torch.from_numpy(sdf.reshape(-1).astype(np.float32)).cuda()
+    iters, ns = 7, 3001
+    idx = torch.empty((iters, ns), dtype=torch.int32, device="cuda")
+    _lib.check(_lib.lib().dj_sample_schedule(s.data_ptr(), s.shape[0], iters, ns, 0.2, 1234, idx.data_ptr(), None))
+    idx = idx.cpu().numpy()
+    sv = sdf.reshape(-1).astype(np.float32)
+    assert idx.min() >= 0 and idx.max() < 40000
+    for e in range(iters):
+        row = idx[e]
+        assert (sv[row[: ns // 2]] > 0).all() and (sv[row[ns // 2:]] <= 0).all()
+        assert len(np.unique(row)) == ns
+    assert not np.array_equal(idx[0], idx[1])
+    frac_uniform = (idx >= 20000).mean()
+    assert 0.1 < frac_uniform < 0.5
+    ones = torch.ones(1000, device="cuda")
+    with pytest.raises(errors.NoSamplesError):
+        _lib.check(_lib.lib().dj_sample_schedule(ones.data_ptr(), 1000, 2, 100, 0.2, 1, idx_dev_ptr(), None))
+
+
+def idx_dev_ptr():
+    t = torch.empty(4096, dtype=torch.int32, device="cuda")
+    idx_dev_ptr.keep = t
+    return t.data_ptr()

@@ -1,0 +1,69 @@
+"""create_mesh drop-in: GPU grid query + GPU marching cubes + f64 post-processing against the
+oracle pipeline run on the SAME f32 grid (topology is only comparable on identical grids)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mc_oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("dims,use_net,level,direction,sigmoid",
+                         [((48, 48, 48), 1, 0.0, "ascent", False), ((40, 32, 24), 0, 0.0, "ascent", False),
+                          ((32, 32, 32), 2, 0.5, "descent", True)])
+def test_create_mesh_equals_oracle_pipeline_on_the_same_grid(precision, dims, use_net, level, direction, sigmoid):
+    from deepjoin_b200.core import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision=precision)
+    code = util.trained_code(0)
+    mesh = R.create_mesh(code, dec, use_net, sigmoid=sigmoid, level=level, gradient_direction=direction, dims=dims,
+                         padding=0.1)
+    values = R.decode_shape(code, dec, dims, use_net=use_net, padding=0.1, reshape=False, sigmoid=sigmoid)
+    values = values.reshape([d for d in dims])
+    vo, fo = mc_oracle.mesh_from_volume(values, level, dims, 0.1, direction)
+    from deepjoin_b200.mesh import Mesh
+    ref = Mesh(vo, fo)
+    assert np.array_equal(mesh.faces, ref.faces)
+    assert np.array_equal(mesh.vertices, ref.vertices)
+    assert mesh.vertices.dtype == np.float64 and len(mesh.faces) > 0
+
+
+def test_create_mesh_raises_isosurface_error_and_worker_makes_empty_mesh(tmp_path):
+    from deepjoin_b200.core import errors, reconstruct as R
+    dec = util.make_decoder(0, "default", precision="fp32")  # degenerate field: no zero crossing
+    code = util.code_for(0, "default")
+    with pytest.raises(errors.IsosurfaceExtractionError):
+        R.create_mesh(code, dec, 0, sigmoid=False, level=0.0, gradient_direction="ascent", dims=(16, 16, 16))
+    with pytest.raises(errors.IsosurfaceExtractionError):
+        R.create_mesh(code, dec, 0, sigmoid=False, level=0.0, gradient_direction="sideways", dims=(16, 16, 16))
+
+
+def test_create_mesh_exports_and_saves_values(tmp_path):
+    from deepjoin_b200.core import reconstruct as R
+    from deepjoin_b200.mesh import load_ply
+    dec = util.make_decoder(1, "trained_norm", precision="bf16")
+    code = util.trained_code(1)
+    f_out, vals = str(tmp_path / "m.ply"), str(tmp_path / "v.npy")
+    mesh = R.create_mesh(code, dec, 1, sigmoid=False, level=0.0, gradient_direction="ascent", f_out=f_out,
+                         save_values=vals, dims=(32, 32, 32))
+    back = load_ply(f_out)
+    assert np.array_equal(back.faces, mesh.faces)
+    v = np.load(vals)
+    assert v.shape == (32, 32, 32) and v.dtype == np.float64
+
+
+def test_full_size_256_mesh_is_consistent():
+    """BASELINE config 2: 256^3 grid + marching cubes; MC of the device grid == oracle MC of the
+    same grid copied to the host."""
+    from deepjoin_b200.core import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision="bf16")
+    code = util.trained_code(0)
+    dims = (256, 256, 256)
+    mesh = R.create_mesh(code, dec, 1, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims)
+    vol = R.decode_shape_device(code, dec, dims, use_net=1, padding=0.1, sigmoid=False).reshape(dims).cpu().numpy()
+    vo, fo = mc_oracle.mesh_from_volume(vol, 0.0, dims, 0.1, "ascent")
+    from deepjoin_b200.mesh import Mesh
+    ref = Mesh(vo, fo)
+    assert np.array_equal(mesh.faces, ref.faces) and np.array_equal(mesh.vertices, ref.vertices)

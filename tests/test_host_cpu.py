@@ -1,0 +1,168 @@
+"""CPU-only checks of the host layer: C-ABI library loads and exports every declared symbol,
+sampler index schedule is bit-exact with the reference's sampler, mesh container, grid
+coordinate arithmetic, drop-in import shims."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from deepjoin_b200 import _lib, build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "deepjoin_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(dj_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert _lib.lib().dj_abi_version() == 1
+
+
+def test_status_codes_map_to_reference_exceptions():
+    from deepjoin_b200 import _lib
+    from deepjoin_b200.core import errors
+    _lib.lib()
+    with pytest.raises(errors.IsosurfaceExtractionError):
+        _lib.check(_lib.ERR_NO_SURFACE)
+    with pytest.raises(errors.IsosurfaceExtractionError):
+        _lib.check(_lib.ERR_LEVEL_RANGE)
+    with pytest.raises(errors.NoSamplesError):
+        _lib.check(_lib.ERR_NO_SAMPLES)
+    with pytest.raises(NotImplementedError):
+        _lib.check(_lib.ERR_UNSUPPORTED)
+    with pytest.raises(RuntimeError):
+        _lib.check(_lib.ERR_BAD_NET)
+    assert issubclass(errors.IsosurfaceExtractionError, RuntimeError)
+
+
+def test_null_arguments_are_rejected_without_a_gpu():
+    from deepjoin_b200 import _lib
+    L = _lib.lib()
+    assert L.dj_query_points(None, None, None, 0, 0, 0, 0, 0, None, None) == _lib.ERR_INVALID
+    assert L.dj_mc_fill(None, 0, None, None, None) == _lib.ERR_INVALID
+    assert b"dj_mc_fill" in L.dj_last_error()
+
+
+def test_sample_indices_match_reference_sampler():
+    from deepjoin_b200.core import data
+    g = np.load(os.path.join(G, "sampler.npz"))
+    pts = np.hstack((g["xyz"], g["n"]))
+    for seed, n, key in ((11, 600, "sel"), (12, 601, "sel2")):
+        np.random.seed(seed)
+        idx = data.select_sample_indices(g["sdf"], n, uniform_ratio=0.2)
+        assert np.array_equal(pts[idx], g[key + "_pts"]) and np.array_equal(g["sdf"][idx], g[key + "_vals"])
+        np.random.seed(seed)
+        p, v = data.select_samples(pts, g["sdf"], n, uniform_ratio=0.2)
+        assert np.array_equal(p, g[key + "_pts"]) and np.array_equal(v, g[key + "_vals"])
+
+
+def test_sampler_raises_no_samples_error():
+    from deepjoin_b200.core import data, errors
+    with pytest.raises(errors.NoSamplesError):
+        data.select_samples(np.random.rand(50, 6), np.ones((50, 1)), 10, uniform_ratio=None)
+
+
+def test_schedule_consumes_rng_like_the_reference_loop():
+    from deepjoin_b200 import reconstruct as R
+    from oracle import decoder_oracle as O
+    g = np.load(os.path.join(G, "sampler.npz"))
+    pts = np.hstack((g["xyz"], g["n"]))
+    np.random.seed(3)
+    sched = R.make_schedule(g["sdf"], 3, 200, 0.2)
+    np.random.seed(3)
+    for e in range(3):
+        p, v = O.select_samples(pts, g["sdf"], 200, uniform_ratio=0.2)
+        assert np.array_equal(pts[sched[e]], p)
+
+
+def test_init_code_matches_reference_rng_use():
+    from deepjoin_b200 import reconstruct as R
+    g = np.load(os.path.join(G, "reconstruct.npz"))
+    torch.manual_seed(5)
+    assert np.array_equal(R.init_code(128, 64, 0.01).numpy(), g["default_code0"])
+
+
+def test_grid_axis_arithmetic_is_numpy_linspace():
+    # the kernels evaluate (t == d-1 ? stop : t*step) - offs in float64 (mlp_tc.cuh lin_axis)
+    for d in (2, 3, 12, 128, 256, 257, 512):
+        for padding in (0.0, 0.1, 0.25):
+            stop, offs = 1.0 + (padding * 2), 0.5 + padding
+            step = stop / (d - 1)
+            t = np.arange(d, dtype=np.float64)
+            mine = np.where(t == d - 1, stop, t * step) - offs
+            ref = np.linspace(0, 1.0 + (padding * 2), d) - (0.5 + padding)
+            assert np.array_equal(mine, ref)
+
+
+def test_mesh_container(tmp_path):
+    from deepjoin_b200.mesh import Mesh, load_ply
+    v = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 0, 0], [np.nan, 0, 0]], dtype=np.float64)
+    f = np.array([[0, 1, 2], [0, 3, 2], [0, 1, 4]])
+    m = Mesh(v, f)
+    assert len(m.vertices) == 3 and m.faces.tolist() == [[0, 1, 2], [0, 1, 2]]
+    raw = Mesh(v[:4], f[:2], process=False)
+    assert len(raw.vertices) == 4
+    path = str(tmp_path / "m.ply")
+    m.export(path)
+    back = load_ply(path)
+    assert np.allclose(back.vertices, m.vertices) and np.array_equal(back.faces, m.faces)
+    m.export(str(tmp_path / "m.obj"))
+    assert Mesh().is_empty
+    Mesh().export(str(tmp_path / "e.ply"))
+
+
+def test_decoder_rejects_unsupported_configurations():
+    from deepjoin_b200.networks.decoder_z_lb_both_leaky_n_sdf import Decoder
+    from tests.util import SPECS
+    base = dict(latent_size=128, tool_latent_size=64, num_dims=3, **SPECS["NetworkSpecs"], **SPECS["SubnetSpecs"])
+    for bad in (dict(use_tanh=True), dict(xyz_in_all=True), dict(latent_in=[2, 4]), dict(num_dims=2),
+                dict(subnet_xyz=False), dict(dims=[256] * 8)):
+        kw = dict(base)
+        kw.update(bad)
+        with pytest.raises(NotImplementedError):
+            Decoder(**kw)
+    dec = Decoder(**base)
+    keys = set(dec.state_dict())
+    assert {"lin0.weight_g", "lin0.weight_v", "lin0.bias", "lin8.weight", "hnet_lin5.weight", "hnet_lin4.weight_g"} <= keys
+    assert dec.lin3.weight_v.shape == (381, 512) and dec.lin4.weight_v.shape == (512, 512)
+    with pytest.raises(NotImplementedError):  # training mode has no kernel
+        dec.train()._check_eval()
+    with pytest.raises(RuntimeError):
+        dec.eval().forward(torch.zeros(2, 195), use_net=7)
+    with pytest.raises(NotImplementedError):
+        dec.forward(torch.zeros(2, 195), return_normals=True)
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "deepjoin_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "oracle/" in txt:
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad
+
+
+def test_dropin_import_names():
+    code = ("import core, core.reconstruct, core.errors, core.data, networks.decoder_z_lb_both_leaky_n_sdf as n;"
+            "import deepjoin_b200.core as c;"
+            "from reconstruct import reconstruct;"
+            "assert core.errors.IsosurfaceExtractionError is c.errors.IsosurfaceExtractionError;"
+            "assert core.reconstruct.create_mesh is c.reconstruct.create_mesh;"
+            "a = __import__('networks.' + 'decoder_z_lb_both_leaky_n_sdf', fromlist=['Decoder']);"
+            "assert a.Decoder is n.Decoder; print('ok')")
+    env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "deepjoin_b200", "dropin"))
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr

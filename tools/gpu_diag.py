@@ -1,0 +1,183 @@
+"""Stage-by-stage GPU diagnostics, each stage in its own subprocess (a device trap in one stage must
+not poison the others).  Writes gpurun_out/diag.json.  Usage: python tools/gpu_diag.py [stage ...]"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def bf16_round(a):
+    import numpy as np
+    u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+def stage_probe():
+    import ctypes
+    import numpy as np
+    from deepjoin_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    res = {}
+    for K in (64, 256):
+        A = rng.standard_normal((128, K)).astype(np.float32)
+        W = rng.standard_normal((128, K)).astype(np.float32)
+        ref = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
+        for bulk in (0, 1):
+            D = np.zeros((128, 128), np.float32)
+            rc = L.dj_debug_umma_probe(A.ctypes.data, W.ctypes.data, K, bulk, 0, 0, 0, D.ctypes.data)
+            key = "K%d_bulk%d" % (K, bulk)
+            if rc:
+                res[key] = {"rc": rc, "err": _lib.last_error()}
+                continue
+            err = np.abs(D - ref)
+            res[key] = {"rc": 0, "max_err": float(err.max()), "ref_absmax": float(np.abs(ref).max()),
+                        "frac_close": float((err < 1e-2 * max(1.0, np.abs(ref).max())).mean()),
+                        "nan": int(np.isnan(D).sum())}
+            if err.max() > 1e-2:
+                # pattern hints: which rows / columns are right
+                ok = err < 1e-2
+                res[key]["rows_ok"] = int(ok.all(axis=1).sum())
+                res[key]["cols_ok"] = int(ok.all(axis=0).sum())
+                res[key]["D00"] = [float(x) for x in D[0, :4]]
+                res[key]["ref00"] = [float(x) for x in ref[0, :4]]
+    return res
+
+
+def _fwd_errors(precision, kind, n=8192):
+    import numpy as np
+    import torch
+    from oracle import decoder_oracle as O, synth
+    from tests import util
+    dec = util.make_decoder(0, kind, precision=precision)
+    net = util.oracle_net(0, kind, "float64")
+    code = util.code_for(0, kind)
+    pts = synth.make_points(n, 1)
+    out = {}
+    for u in (0, 3, 1, 2):
+        ref = O.forward(net, code.double(), pts.double(), u).numpy()
+        t0 = time.time()
+        got = dec.query(code.cuda(), pts.cuda(), use_net=u).cpu().numpy()
+        e = np.abs(got - ref)
+        out["u%d" % u] = {"max": float(e.max()), "mean": float(e.mean()), "nan": int(np.isnan(got).sum()),
+                          "ref_std": float(ref.std()), "t": time.time() - t0}
+    ref = [o.numpy() for o in O.forward_all(net, code.double(), pts.double())]
+    got = [o.cpu().numpy() for o in dec.query_all(code.cuda(), pts.cuda())]
+    out["all20_max"] = [float(np.abs(g - r).max()) for g, r in zip(got, ref)]
+    return out
+
+
+def stage_fp32():
+    return {k: _fwd_errors("fp32", k) for k in ("default", "trained_norm")}
+
+
+def stage_tc():
+    return {k: _fwd_errors("bf16", k) for k in ("default", "trained_norm")}
+
+
+def stage_mc():
+    import numpy as np
+    import torch
+    from oracle import mc_oracle
+    from deepjoin_b200.core import reconstruct as R
+    res = {}
+    rng = np.random.default_rng(0)
+    for name, vol in (("noise", rng.uniform(-1, 1, (20, 21, 22)).astype(np.float32)),
+                      ("sphere", (np.sqrt(((np.indices((48, 48, 48)) - 23.5) ** 2).sum(0)) - 15).astype(np.float32))):
+        vo, fo = mc_oracle.marching_cubes(vol, 0.0, "ascent")
+        v, f = R.marching_cubes(torch.from_numpy(vol).cuda(), 0.0, "ascent")
+        v, f = v.cpu().numpy(), f.cpu().numpy()
+        res[name] = {"nv": [len(v), len(vo)], "nf": [len(f), len(fo)],
+                     "faces_equal": bool(f.shape == fo.shape and np.array_equal(f, fo)),
+                     "verts_equal": bool(v.shape == vo.shape and np.array_equal(v.view(np.uint32), vo.view(np.uint32)))}
+        if v.shape == vo.shape and not res[name]["verts_equal"]:
+            res[name]["vert_max_diff"] = float(np.abs(v - vo).max())
+    return res
+
+
+def stage_latent():
+    import numpy as np
+    import torch
+    from oracle import decoder_oracle as O, synth
+    from tests import util
+    from deepjoin_b200 import reconstruct as RR
+    res = {}
+    xyz, sdf, nrm = synth.make_sample_set(4000, seed=1)
+    x = torch.from_numpy(xyz[:1000].astype(np.float32))
+    s = torch.from_numpy(sdf[:1000].astype(np.float32))
+    n = torch.from_numpy(nrm[:1000].astype(np.float32))
+    for kind in ("default", "trained_norm"):
+        dec = util.make_decoder(0, kind, precision="fp32")
+        code = util.code_for(0, kind)
+        g, t = RR.latent_grad(dec, code.cuda(), x.cuda(), s.cuda(), n.cuda())
+        gr, tr = O.latent_grad(util.oracle_net(0, kind), code, x, s, n)
+        res[kind] = {"rel_err": float((g.cpu() - gr).abs().max() / gr.abs().max()), "terms": [float(v) for v in t.cpu()],
+                     "terms_ref": tr}
+    return res
+
+
+def stage_timing():
+    """First timings: grid query at 128^3 / 256^3 per precision, MC, latent step."""
+    import torch
+    from tests import util
+    from deepjoin_b200.core import reconstruct as R
+    res = {}
+    code = util.trained_code(0)
+    for precision, dimlist in (("bf16", (128, 256)), ("fp32", (64,))):
+        dec = util.make_decoder(0, "trained_norm", precision=precision)
+        for d in dimlist:
+            for u in (1, 0):
+                R.decode_shape_device(code, dec, (d, d, d), use_net=u, padding=0.1, sigmoid=False)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                vol = R.decode_shape_device(code, dec, (d, d, d), use_net=u, padding=0.1, sigmoid=False)
+                e1.record()
+                torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1)
+                res["%s_grid%d_u%d" % (precision, d, u)] = {"ms": ms, "q_per_s": d ** 3 / ms * 1e3}
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            R.marching_cubes(vol.reshape(d, d, d), 0.0, "ascent")
+            e0.record()
+            v, f = R.marching_cubes(vol.reshape(d, d, d), 0.0, "ascent")
+            e1.record()
+            torch.cuda.synchronize()
+            res["%s_mc%d" % (precision, d)] = {"ms": e0.elapsed_time(e1), "nv": int(v.shape[0]), "nf": int(f.shape[0])}
+    return res
+
+
+STAGES = {"probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
+          "timing": stage_timing}
+
+if __name__ == "__main__":
+    if len(sys.argv) > 2 and sys.argv[1] == "--run":
+        try:
+            print("DIAG_RESULT " + json.dumps(STAGES[sys.argv[2]]()))
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            traceback.print_exc()
+            print("DIAG_RESULT " + json.dumps({"exception": repr(e)}))
+        sys.exit(0)
+    os.makedirs(OUT, exist_ok=True)
+    stages = sys.argv[1:] or list(STAGES)
+    results = {}
+    for st in stages:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, os.path.abspath(__file__), "--run", st], capture_output=True, text=True,
+                               timeout=300, cwd=ROOT)
+            line = [l for l in p.stdout.splitlines() if l.startswith("DIAG_RESULT ")]
+            results[st] = json.loads(line[-1][12:]) if line else {"rc": p.returncode, "stderr": p.stderr[-2000:], "stdout": p.stdout[-500:]}
+            if line and p.stderr.strip() and "exception" in results[st]:
+                results[st]["stderr"] = p.stderr[-2000:]
+        except subprocess.TimeoutExpired:
+            results[st] = {"timeout": True}
+        results[st]["_sec"] = round(time.time() - t0, 1)
+        print(st, json.dumps(results[st])[:1500], flush=True)
+        json.dump(results, open(os.path.join(OUT, "diag.json"), "w"), indent=1)
