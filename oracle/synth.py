@@ -80,7 +80,8 @@ def make_state_dict(seed=0, kind="default", prefix="", **arch):
 
 def _center_sdf_heads(sd, a, seed):
     from . import decoder_oracle as O
-    code = make_code(seed, a["latent_size"], a["tool_latent_size"])
+    code = trained_code(seed) if (a["latent_size"], a["tool_latent_size"]) == (128, 64) else \
+        make_code(seed, a["latent_size"], a["tool_latent_size"])
     lin = np.linspace(-0.55, 0.55, 24)
     pts = torch.tensor(np.stack(np.meshgrid(lin, lin, lin, indexing="ij"), -1).reshape(-1, 3), dtype=torch.float64)
     net = O.fold(sd, dtype=torch.float64, **a)
@@ -89,6 +90,13 @@ def _center_sdf_heads(sd, a, seed):
     # hnet: the head passes through LeakyReLU; shift the pre-activation median
     pre_t = O.raw_heads(net, code.double(), pts, h_pre=True)[1]
     sd["hnet_lin%d.bias" % (a["h_layers"] - 1)][0] -= float(pre_t[:, 0].median())
+
+
+def trained_code(seed=0):
+    """Row `seed` of the reference's shipped LatentCodes/2000.pth || 2000_tool.pth (first 8 rows are
+    committed as tests/golden/latent_rows.npz) -- the code the trained-norm weights are centred on."""
+    rows = np.load(os.path.join(GOLDEN, "latent_rows.npz"))
+    return torch.from_numpy(np.concatenate([rows["c2000"][seed % 8], rows["c2000_tool"][seed % 8]]))
 
 
 def make_code(seed=0, latent_size=128, tool_latent_size=64, std=0.0623):
