@@ -31,6 +31,7 @@ struct DjPack {
   // workspaces (grow only)
   DevBuf ws_fwd, ws_lat, ws_host, ws_vol;
   bool tc_attr_set = false;
+  int tc_cluster = 2;  // CTAs sharing one weight stream (1, 2 or 4); env DEEPJOIN_B200_CLUSTER
 };
 
 static void free_pack(DjPack* p) {
@@ -96,6 +97,10 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
   p->desc = *d;
   p->device = device;
   p->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("DEEPJOIN_B200_CLUSTER")) {
+    const int c = atoi(e);
+    if (c == 1 || c == 2 || c == 4) p->tc_cluster = c;
+  }
   p->L = L; p->Lb = Lb; p->H = H; p->K3 = K3;
   auto bail = [&](int code) { free_pack(p); return code; };
 
@@ -278,10 +283,6 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
   int rc;
   if ((rc = launch_fold(p, code_dev, st))) return rc;
   if (precision == DJ_PREC_BF16) {
-    if (!p->tc_attr_set) {
-      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-      p->tc_attr_set = true;
-    }
     tc::TcParams P;
     memset(&P, 0, sizeof P);
     P.nets[0] = p->nets[0];
@@ -299,8 +300,29 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     P.out = out_dev;
     P.err = p->err;
     const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
-    const int grid = (int)std::min<int64_t>(ntiles, p->num_sms);
-    tc::tc_forward_kernel<<<grid, tc::NTHREADS, tc::SMEM_BYTES, st>>>(P);
+    int cluster = p->tc_cluster;
+    int grid = (int)std::min<int64_t>((ntiles + cluster - 1) / cluster * cluster, p->num_sms / cluster * cluster);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(tc::NTHREADS);
+    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    auto kern = cluster == 4 ? tc::tc_forward_kernel<4> : (cluster == 2 ? tc::tc_forward_kernel<2> : tc::tc_forward_kernel<1>);
+    if (!p->tc_attr_set) {
+      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
+      p->tc_attr_set = true;
+    }
+    DJ_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     DJ_LAUNCHED();
     return DJ_OK;
   }

@@ -16,8 +16,9 @@
 //     MMAs start while the drain is still running;
 //   * heads (tanh / sigmoid / B,R combine) in the last epilogue; 4 B per point leave the SM.
 //
-// Warp roles (192 threads): warp 0 = weight producer, warp 1 = MMA issuer (one thread) + TMEM
-// allocation, warps 2..5 = epilogue (one TMEM lane quarter each, one point per thread).
+// Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer (one thread) + TMEM
+// allocation, warps 2..9 = epilogue (TMEM lane quarter = warp % 4; two warps share a quarter and
+// split every 64-column group 32/32).  CTAs of a cluster share one weight stream by multicast.
 #pragma once
 #include "common.cuh"
 #include "ptx.cuh"
@@ -33,7 +34,8 @@ constexpr int A_CHUNK_BYTES = TILE_M * KCH * 2;  // 16 KB
 constexpr int STAGE_BYTES = NCH * KCH * 2;       // 16 KB
 constexpr int NSTAGES = 5;
 constexpr int MAX_LAYERS = 10;
-constexpr int NTHREADS = 192;
+constexpr int NEPI = 256;                     // epilogue threads (8 warps)
+constexpr int NTHREADS = 64 + NEPI;
 
 constexpr int SM_A = 0;
 constexpr int SM_W = SM_A + 8 * A_CHUNK_BYTES;           // 131072
@@ -98,8 +100,15 @@ __device__ __forceinline__ void grid_point(const TcParams& P, int64_t r, float& 
 
 __device__ __forceinline__ float leaky(float v, float slope) { return fmaxf(v, v * slope); }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// CLUSTER = number of CTAs that share one weight stream: every CTA fetches 1/CLUSTER of each stage and
+// multicasts it to all (cp.async.bulk ... .multicast::cluster), cutting L2 reads per point by CLUSTER.
+template <int CLUSTER>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_constant__ TcParams P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -117,16 +126,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+  // every CTA of a cluster must consume the same number of weight passes: uniform iteration count,
+  // iterations past the last tile compute on zeros and write nothing
+  const int64_t iters = (ntiles + gridDim.x - 1) / gridDim.x;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CLUSTER) - 1u);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < NSTAGES; s++) {
       ptx::mbar_init(W_FULL(s), 1);
-      ptx::mbar_init(W_EMPTY(s), 1);
+      ptx::mbar_init(W_EMPTY(s), CLUSTER);
     }
-    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(c), 128);
+    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(c), NEPI);
     for (int j = 0; j < 4; j++) {
       ptx::mbar_init(ACC_FULL(j), 1);
-      ptx::mbar_init(ACC_EMPTY(j), 128);
+      ptx::mbar_init(ACC_EMPTY(j), NEPI);
     }
     ptx::mbar_fence_init();
   }
@@ -136,84 +149,99 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();  // peers' barriers are initialised before anything is multicast to them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
     // ===================== weight producer (TMA engine, 1-D bulk copies) =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int net = 0; net < 2; net++) {
-          if (!((P.net_mask >> net) & 1)) continue;
-          const TcNet& N = P.nets[net];
-          const uint8_t* src = N.stream;
-          for (int l = 0; l < N.n_layers; l++) {
-            const int ns = N.layers[l].n_chunks * N.layers[l].k_chunks;
-            const uint32_t bytes = (uint32_t)N.layers[l].stage_bytes;
-            for (int s = 0; s < ns; s++) {
-              ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage);
+    // warp-uniform control flow; one elected lane arms the barrier and issues the copy
+    const uint32_t rank = CLUSTER > 1 ? ptx::cluster_ctarank() : 0u;
+    uint32_t stage = 0, phase = 0;
+    for (int64_t it = 0; it < iters; it++) {
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const TcNet& N = P.nets[net];
+        const uint8_t* src = N.stream;
+        for (int l = 0; l < N.n_layers; l++) {
+          const int ns = N.layers[l].n_chunks * N.layers[l].k_chunks;
+          const uint32_t bytes = (uint32_t)N.layers[l].stage_bytes;
+          const uint32_t part = bytes / CLUSTER;
+          for (int s = 0; s < ns; s++) {
+            ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage);  // every CTA of the cluster freed the slot
+            if (ptx::elect_one()) {
               ptx::mbar_expect_tx(W_FULL(stage), bytes);
-              ptx::bulk_g2s(sW + stage * STAGE_BYTES, src, bytes, W_FULL(stage));
-              src += bytes;
+              if (CLUSTER > 1)
+                ptx::bulk_g2s_multicast(sW + stage * STAGE_BYTES + rank * part, src + rank * part, part, W_FULL(stage), CMASK);
+              else
+                ptx::bulk_g2s(sW + stage * STAGE_BYTES, src, bytes, W_FULL(stage));
+            }
+            __syncwarp();
+            src += bytes;
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // The whole warp runs the (warp-uniform) loop so addresses / descriptors live in uniform
+    // registers; one elected lane issues tcgen05.mma / tcgen05.commit.
+    const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
+    const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
+    const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
+    uint32_t stage = 0, phase = 0, a_ph = 0, e_ph = 0;
+    for (int64_t it = 0; it < iters; it++) {
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const TcNet& N = P.nets[net];
+        for (int l = 0; l < N.n_layers; l++) {
+          const TcLayer L = N.layers[l];
+          const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)L.mma_n);
+          for (int j = 0; j < L.n_chunks; j++) {
+            ptx::mbar_wait(ACC_EMPTY(j), ((e_ph >> j) & 1) ^ 1, P.err, 0x200 | j);
+            e_ph ^= 1u << j;
+            const uint32_t d_tmem = tmem_base + (uint32_t)(j * NCH);
+            for (int c = 0; c < L.k_chunks; c++) {
+              if (j == 0) {
+                ptx::mbar_wait(A_READY(c), (a_ph >> c) & 1, P.err, 0x300 | c);
+                a_ph ^= 1u << c;
+              }
+              ptx::mbar_wait(W_FULL(stage), phase, P.err, 0x400 | stage);
+              ptx::tc_fence_after();
+              const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
+              const uint64_t bd = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+              if (ptx::elect_one()) {
+#pragma unroll
+                for (int k = 0; k < KCH / 16; k++)
+                  ptx::mma_f16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+                if (CLUSTER > 1) ptx::mma_commit_multicast(W_EMPTY(stage), CMASK);
+                else ptx::mma_commit(W_EMPTY(stage));
+                if (c == L.k_chunks - 1) ptx::mma_commit(ACC_FULL(j));
+              }
+              __syncwarp();
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
             }
           }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer (single thread) =====================
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, a_ph = 0, e_ph = 0;
-      for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        for (int net = 0; net < 2; net++) {
-          if (!((P.net_mask >> net) & 1)) continue;
-          const TcNet& N = P.nets[net];
-          for (int l = 0; l < N.n_layers; l++) {
-            const TcLayer L = N.layers[l];
-            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)L.mma_n);
-            for (int j = 0; j < L.n_chunks; j++) {
-              ptx::mbar_wait(ACC_EMPTY(j), ((e_ph >> j) & 1) ^ 1, P.err, 0x200 | j);
-              e_ph ^= 1u << j;
-              ptx::tc_fence_after();
-              const uint32_t d_tmem = tmem_base + (uint32_t)(j * NCH);
-              for (int c = 0; c < L.k_chunks; c++) {
-                if (j == 0) {
-                  ptx::mbar_wait(A_READY(c), (a_ph >> c) & 1, P.err, 0x300 | c);
-                  a_ph ^= 1u << c;
-                }
-                ptx::mbar_wait(W_FULL(stage), phase, P.err, 0x400 | stage);
-                ptx::tc_fence_after();
-                const uint32_t a_addr = sA + c * A_CHUNK_BYTES;
-                const uint32_t b_addr = sW + stage * STAGE_BYTES;
-#pragma unroll
-                for (int k = 0; k < KCH / 16; k++) {
-                  ptx::mma_f16_ss(d_tmem, ptx::umma_desc_sw128_kmajor(a_addr + k * 32),
-                                  ptx::umma_desc_sw128_kmajor(b_addr + k * 32), idesc, (uint32_t)((c | k) != 0));
-                }
-                ptx::mma_commit(W_EMPTY(stage));
-                if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
-              }
-              ptx::mma_commit(ACC_FULL(j));
-            }
-          }
-        }
-      }
-    }
   } else {
-    // ===================== epilogue warps: one point per thread =====================
-    const int q = warp & 3;
+    // ===================== epilogue: 8 warps, a point per thread pair (32-column halves) ==========
+    const int q = warp & 3;              // TMEM lane quarter this warp may read
+    const int h = (warp - 2) >> 2;       // which 32 columns of every 64-column group
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 64;  // 0..127 among epilogue threads
+    const int et = threadIdx.x - 64;     // 0..255 among epilogue threads
     const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
     const uint32_t a_row = sA + row * 128;
     const int sw = row & 7;
     const float slope = P.head.slope;
+    const uint64_t slope2 = ptx::pack_f32x2(slope, slope);
     uint32_t f_ph = 0;
     int bias_buf = 0;
 
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    for (int64_t it = 0; it < iters; it++) {
+      const int64_t tile = it * gridDim.x + blockIdx.x;
       const int64_t g = tile * TILE_M + row;
       float x = 0.f, y = 0.f, z = 0.f;
       if (g < P.n) {
@@ -229,29 +257,25 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
         epi_bar();  // everybody is past the previous use of sTab / sBias
         {
           const float4* t = P.tables + N.l0_table * 512;
-#pragma unroll
-          for (int i = 0; i < 4; i++) sTab[et + 128 * i] = __ldg(t + et + 128 * i);
-          if (N.layers[0].kind == KIND_HIDDEN) {
-            const float4 b = __ldg(reinterpret_cast<const float4*>(P.bias + N.layers[0].bias_off) + et);
-            reinterpret_cast<float4*>(sBias + bias_buf * 512)[et] = b;
-          }
+          sTab[et] = __ldg(t + et);
+          sTab[et + 256] = __ldg(t + et + 256);
+          if (N.layers[0].kind == KIND_HIDDEN)
+            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] =
+                __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[0].bias_off) + et);
         }
         epi_bar();
 #pragma unroll 1
         for (int c = 0; c < 8; c++) {
 #pragma unroll
-          for (int gq = 0; gq < 8; gq++) {
+          for (int gq = 0; gq < 4; gq++) {
             float v[8];
 #pragma unroll
             for (int f = 0; f < 8; f++) {
-              const float4 t = sTab[c * 64 + gq * 8 + f];
+              const float4 t = sTab[c * 64 + h * 32 + gq * 8 + f];
               v[f] = leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
             }
-            const uint32_t dst = a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4);
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ptx::pack_bf16x2(v[0], v[1])),
-                         "r"(ptx::pack_bf16x2(v[2], v[3])), "r"(ptx::pack_bf16x2(v[4], v[5])),
-                         "r"(ptx::pack_bf16x2(v[6], v[7]))
-                         : "memory");
+            st_shared_v4(a_row + c * A_CHUNK_BYTES + (((4 * h + gq) ^ sw) << 4), ptx::pack_bf16x2(v[0], v[1]),
+                         ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
           }
           ptx::fence_proxy_async_smem();
           ptx::mbar_arrive(A_READY(c));
@@ -265,29 +289,33 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
           if (L.kind == KIND_HEAD) {
             f_ph ^= 1u;
             uint32_t r[8];
-            ptx::tmem_ld8(tmem_lane, r);
-            ptx::tmem_wait_ld();
+            if (h == 0) {
+              ptx::tmem_ld8(tmem_lane, r);
+              ptx::tmem_wait_ld();
+            }
             ptx::tc_fence_before();
             ptx::mbar_arrive(ACC_EMPTY(0));
-            float* dst = net == 0 ? yc : yt;
+            if (h == 0) {
+              float* dst = net == 0 ? yc : yt;
 #pragma unroll
-            for (int i = 0; i < 5; i++) {
-              float v = __uint_as_float(r[i]) + __ldg(P.bias + L.bias_off + i);
-              dst[i] = N.head_leaky ? leaky(v, slope) : v;
+              for (int i = 0; i < 5; i++) {
+                const float v = __uint_as_float(r[i]) + __ldg(P.bias + L.bias_off + i);
+                dst[i] = N.head_leaky ? leaky(v, slope) : v;
+              }
             }
             continue;
           }
           epi_bar();  // all epilogue warps finished the previous drain: smem tables may be rewritten
           // prefetch what the NEXT layer's drain needs
-          const bool has_next = (l + 1 < N.n_layers);
-          const int next_kind = has_next ? N.layers[l + 1].kind : -1;
-          float4 pre_b = make_float4(0, 0, 0, 0), pre_t[4];
+          const int next_kind = (l + 1 < N.n_layers) ? N.layers[l + 1].kind : -1;
+          float2 pre_b = make_float2(0.f, 0.f);
+          float4 pre_t0 = make_float4(0, 0, 0, 0), pre_t1 = pre_t0;
           if (next_kind == KIND_HIDDEN) {
-            pre_b = __ldg(reinterpret_cast<const float4*>(P.bias + N.layers[l + 1].bias_off) + et);
+            pre_b = __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[l + 1].bias_off) + et);
           } else if (next_kind == KIND_HIDDEN_XYZ) {
             const float4* t = P.tables + N.layers[l + 1].table * 512;
-#pragma unroll
-            for (int i = 0; i < 4; i++) pre_t[i] = __ldg(t + et + 128 * i);
+            pre_t0 = __ldg(t + et);
+            pre_t1 = __ldg(t + et + 256);
           }
           const float* bias = sBias + bias_buf * 512;
           for (int j = 0; j <= last; j++) {
@@ -295,10 +323,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
             f_ph ^= 1u << j;
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
-              const int col0 = j * NCH + half * 64;
-              uint32_t r0[32], r1[32];
-              ptx::tmem_ld32(tmem_lane + col0, r0);
-              ptx::tmem_ld32(tmem_lane + col0 + 32, r1);
+              const int col0 = j * NCH + half * 64 + h * 32;
+              uint32_t r[32];
+              ptx::tmem_ld32(tmem_lane + col0, r);
               ptx::tmem_wait_ld();
               if (half == 1) {
                 ptx::tc_fence_before();
@@ -306,24 +333,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
               }
               const int c = 2 * j + half;
 #pragma unroll
-              for (int gq = 0; gq < 8; gq++) {
-                float v[8];
+              for (int gq = 0; gq < 4; gq++) {
+                uint32_t pk[4];
+                if (L.kind == KIND_HIDDEN_XYZ) {
 #pragma unroll
-                for (int f = 0; f < 8; f++) {
-                  const int i = gq * 8 + f;
-                  const float acc = __uint_as_float(i < 32 ? r0[i] : r1[i - 32]);
-                  if (L.kind == KIND_HIDDEN_XYZ) {
-                    const float4 t = sTab[col0 + i];
-                    v[f] = leaky(acc + fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
-                  } else {
-                    v[f] = leaky(acc + bias[col0 + i], slope);
+                  for (int f = 0; f < 8; f += 2) {
+                    const float4 t0 = sTab[col0 + gq * 8 + f], t1 = sTab[col0 + gq * 8 + f + 1];
+                    const float v0 = leaky(__uint_as_float(r[gq * 8 + f]) + fmaf(t0.x, x, fmaf(t0.y, y, fmaf(t0.z, z, t0.w))), slope);
+                    const float v1 = leaky(__uint_as_float(r[gq * 8 + f + 1]) + fmaf(t1.x, x, fmaf(t1.y, y, fmaf(t1.z, z, t1.w))), slope);
+                    pk[f >> 1] = ptx::pack_bf16x2(v0, v1);
+                  }
+                } else {
+                  const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
+                  const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8 + 4);
+                  const uint64_t bb[4] = {ptx::pack_f32x2(b0.x, b0.y), ptx::pack_f32x2(b0.z, b0.w),
+                                          ptx::pack_f32x2(b1.x, b1.y), ptx::pack_f32x2(b1.z, b1.w)};
+#pragma unroll
+                  for (int f = 0; f < 4; f++) {
+                    const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                    const uint64_t t = ptx::add_f32x2(acc, bb[f]);       // FADD2
+                    const uint64_t u = ptx::mul_f32x2(t, slope2);        // FMUL2
+                    pk[f] = ptx::pack_bf16x2(fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u)), fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u)));
                   }
                 }
-                const uint32_t dst = a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4);
-                asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(ptx::pack_bf16x2(v[0], v[1])),
-                             "r"(ptx::pack_bf16x2(v[2], v[3])), "r"(ptx::pack_bf16x2(v[4], v[5])),
-                             "r"(ptx::pack_bf16x2(v[6], v[7]))
-                             : "memory");
+                st_shared_v4(a_row + c * A_CHUNK_BYTES + (((4 * h + gq) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
               }
               ptx::fence_proxy_async_smem();
               ptx::mbar_arrive(A_READY(c));
@@ -332,19 +365,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
           // publish the prefetched tables for the next drain (made visible by its epi_bar)
           if (next_kind == KIND_HIDDEN) {
             bias_buf ^= 1;
-            reinterpret_cast<float4*>(sBias + bias_buf * 512)[et] = pre_b;
+            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = pre_b;
           } else if (next_kind == KIND_HIDDEN_XYZ) {
-#pragma unroll
-            for (int i = 0; i < 4; i++) sTab[et + 128 * i] = pre_t[i];
+            sTab[et] = pre_t0;
+            sTab[et + 256] = pre_t1;
           }
         }
       }
-      if (g < P.n) write_heads(P.head, yc, yt, P.out, g);
+      if (h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
     }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CLUSTER > 1) ptx::cluster_sync();  // nobody exits while a peer may still signal its barriers
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 

@@ -48,16 +48,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 
 // Bounded wait: a protocol bug must not hang the GPU.  On timeout the error word is set
 // and the kernel traps (the host reports DJ_ERR_DEVICE / a CUDA error instead of hanging).
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_word, uint32_t tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+// slow path kept out of line so that the common case (barrier already complete, or completing
+// within try_wait's own hardware wait) costs two instructions at the call site
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, unsigned int* err_word, uint32_t tag) {
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      if (err_word) atomicExch(err_word, 0xDEAD0000u | tag);
-      __threadfence_system();
-      __trap();
+    if ((++spins & 0xFFFFu) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 8000000000LL) {
+        if (err_word) atomicExch(err_word, 0xDEAD0000u | tag);
+        __threadfence_system();
+        __trap();
+      }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned int* err_word, uint32_t tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, err_word, tag);
 }
 
 // ---------------------------------------------------------------- async proxy
@@ -71,6 +81,27 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
                "l"(src), "r"(bytes), "r"(bar)
                : "memory");
+}
+
+// multicast variant: the bytes land at the same CTA-relative offset in every CTA of `mask`, and each
+// of those CTAs' mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar,
+                                                   uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst_smem),
+      "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+      : "memory");
+}
+
+// ---------------------------------------------------------------- clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
 // ---------------------------------------------------------------- tcgen05 / TMEM
@@ -101,6 +132,13 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
 // implies tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// same, arriving on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_multicast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(mask)
+               : "memory");
 }
 
 // warp w reads TMEM lanes [32*(w%4), +32): thread t gets lane t, 32 consecutive columns
@@ -143,6 +181,23 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
+
+// packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100)
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ float f32x2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float f32x2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
 // packed bf16x2 from two floats (lo -> low half)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
