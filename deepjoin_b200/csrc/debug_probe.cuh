@@ -14,7 +14,7 @@ struct ProbeParams {
   const uint8_t* Bblob;  // K/64 pre-swizzled [128 x 64] bf16 tiles (pack_tile layout)
   float* D;              // [128, 128] fp32 out
   int K;                 // multiple of 64, <= 256
-  int use_bulk;          // 1: cp.async.bulk for B, 0: generic loads + proxy fence
+  int use_bulk;          // bit 0: cp.async.bulk for B (else generic loads + proxy fence); bit 1: A operand in TMEM
   int k_adv_bytes;       // start-address advance per K=16 step (32)
   uint32_t idesc;
   uint64_t desc_tmpl;    // descriptor without the address field
@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
     ptx::mbar_fence_init();
   }
   if (warp == 0) {
-    ptx::tmem_alloc(ptx::smem_u32((const void*)slot), 128);
+    ptx::tmem_alloc(ptx::smem_u32((const void*)slot), 256);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -53,7 +53,21 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
                    "r"(ptx::pack_bf16x2(a[2], a[3])), "r"(ptx::pack_bf16x2(a[4], a[5])), "r"(ptx::pack_bf16x2(a[6], a[7]))
                    : "memory");
     }
-  if (P.use_bulk) {
+  const bool a_tmem = (P.use_bulk & 2) != 0;
+  if (a_tmem) {
+    // the epilogue's tensor-memory store of mlp_tc.cuh: bf16 pairs, TMEM lane = row, columns 128 + k/2
+    for (int c = 0; c < kc; c++)
+      for (int hh = 0; hh < 2; hh++) {
+        uint32_t pk[16];
+        const float* a = P.A + (size_t)row * P.K + c * 64 + hh * 32;
+#pragma unroll
+        for (int i = 0; i < 16; i++) pk[i] = ptx::pack_bf16x2(a[2 * i], a[2 * i + 1]);
+        ptx::tmem_st16(tmem + ((uint32_t)(warp * 32) << 16) + 128u + (uint32_t)(c * 32 + hh * 16), pk);
+      }
+    ptx::tmem_wait_st();
+    ptx::tc_fence_before();
+  }
+  if (P.use_bulk & 1) {
     if (threadIdx.x == 0) {
       ptx::mbar_expect_tx(bar_w, (uint32_t)(kc * 16384));
       for (int c = 0; c < kc; c++) ptx::bulk_g2s(sB + c * 16384, P.Bblob + (size_t)c * 16384, 16384, bar_w);
@@ -66,13 +80,14 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
   ptx::fence_proxy_async_smem();
   __syncthreads();
   if (threadIdx.x == 0) {
-    if (P.use_bulk) ptx::mbar_wait(bar_w, 0, P.err, 0x701);
+    if (P.use_bulk & 1) ptx::mbar_wait(bar_w, 0, P.err, 0x701);
     ptx::tc_fence_after();
     for (int c = 0; c < kc; c++)
       for (int k = 0; k < 4; k++) {
         const uint64_t ad = P.desc_tmpl | (uint64_t)(((sA + c * 16384 + k * P.k_adv_bytes) & 0x3FFFF) >> 4);
         const uint64_t bd = P.desc_tmpl | (uint64_t)(((sB + c * 16384 + k * P.k_adv_bytes) & 0x3FFFF) >> 4);
-        ptx::mma_f16_ss(tmem, ad, bd, P.idesc, (uint32_t)((c | k) != 0));
+        if (a_tmem) ptx::mma_f16_ts(tmem, tmem + 128u + (uint32_t)(c * 32 + k * 8), bd, P.idesc, (uint32_t)((c | k) != 0));
+        else ptx::mma_f16_ss(tmem, ad, bd, P.idesc, (uint32_t)((c | k) != 0));
       }
     ptx::mma_commit(bar_d);
   }
@@ -88,7 +103,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const __grid_constan
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 0) ptx::tmem_dealloc(tmem, 128);
+  if (warp == 0) ptx::tmem_dealloc(tmem, 256);
 }
 
 }  // namespace probe

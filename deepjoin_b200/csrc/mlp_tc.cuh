@@ -7,13 +7,15 @@
 // activations ever leaving the SM:
 //   * the latent columns of lin0 / lin4 / hnet_lin0 are folded into per-shape constants by
 //     fold_kernel (mlp_simt.cuh); the remaining K=3 xyz products run on CUDA cores;
-//   * every 512-wide layer is a 128 x N x K bf16 GEMM: A = activations in shared memory
-//     (K-major, 128-byte swizzle, written by the epilogue), B = weight tiles streamed from L2 by
-//     the TMA engine (cp.async.bulk, 16 KB pre-swizzled stages, mbarrier ring), D = fp32
-//     accumulators in TMEM (4 x 128 columns = all 512 columns);
-//   * epilogue warps drain TMEM 64 columns at a time: + bias, LeakyReLU, -> bf16 -> the A operand
-//     of the next layer, releasing each 64-wide K chunk through an mbarrier so the next layer's
-//     MMAs start while the drain is still running;
+//   * every 512-wide layer is a 128 x N x K bf16 GEMM issued as 128 x 128 x 16 tcgen05.mma:
+//     B = weight tiles streamed from L2 by the TMA engine (cp.async.bulk, 16 KB pre-swizzled stages,
+//     mbarrier ring), D = one of two 128-column fp32 accumulator buffers in TMEM;
+//   * the activations ping-pong between shared memory (K-major, 128-byte swizzle, A operand through
+//     a shared-memory descriptor) and tensor memory (bf16 pairs in TMEM columns [0,256), A operand
+//     read by the tensor core straight from TMEM): layer l reads one and its epilogue writes the
+//     other, so the drain of accumulator chunk j (+ bias, LeakyReLU, -> bf16) runs while the tensor
+//     core computes chunk j+1 of the same layer and the next layer starts on the K chunks that are
+//     already published - the tensor pipe never waits for a whole-layer drain;
 //   * heads (tanh / sigmoid / B,R combine) in the last epilogue; 4 B per point leave the SM.
 //
 // Warp roles (320 threads): warp 0 = weight producer, warp 1 = MMA issuer (one thread) + TMEM
@@ -106,6 +108,10 @@ __device__ __forceinline__ void st_shared_v4(uint32_t dst, uint32_t a, uint32_t 
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// TMEM columns: [0,256) bf16 activations (A operand of odd layers), [256,512) two fp32 accumulator buffers
+constexpr uint32_t TM_A = 0;
+constexpr uint32_t TM_ACC = 256;
+
 // CLUSTER = number of CTAs that share one weight stream: every CTA fetches 1/CLUSTER of each stage and
 // multicasts it to all (cp.async.bulk ... .multicast::cluster), cutting L2 reads per point by CLUSTER.
 template <int CLUSTER>
@@ -119,10 +125,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
   const uint32_t bar0 = base + SM_BAR;
   auto W_FULL = [&](int s) { return bar0 + 8u * s; };
   auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGES + s); };
-  auto A_READY = [&](int c) { return bar0 + 8u * (2 * NSTAGES + c); };
-  auto ACC_FULL = [&](int j) { return bar0 + 8u * (2 * NSTAGES + 8 + j); };
-  auto ACC_EMPTY = [&](int j) { return bar0 + 8u * (2 * NSTAGES + 12 + j); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 16));
+  // A_READY(b, c): K chunk c of the activations in buffer b (0 = shared memory, 1 = tensor memory) is published
+  auto A_READY = [&](int b, int c) { return bar0 + 8u * (2 * NSTAGES + 8 * b + c); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * NSTAGES + 16 + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * NSTAGES + 18 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 20));
+  static_assert(8 * (2 * NSTAGES + 20) + 4 <= 256, "barrier block");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
@@ -136,10 +144,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
       ptx::mbar_init(W_FULL(s), 1);
       ptx::mbar_init(W_EMPTY(s), CLUSTER);
     }
-    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(c), NEPI);
-    for (int j = 0; j < 4; j++) {
-      ptx::mbar_init(ACC_FULL(j), 1);
-      ptx::mbar_init(ACC_EMPTY(j), NEPI);
+    for (int c = 0; c < 16; c++) ptx::mbar_init(A_READY(0, c), NEPI);
+    for (int i = 0; i < 2; i++) {
+      ptx::mbar_init(ACC_FULL(i), 1);
+      ptx::mbar_init(ACC_EMPTY(i), NEPI);
     }
     ptx::mbar_fence_init();
   }
@@ -187,37 +195,49 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) loop so addresses / descriptors live in uniform
     // registers; one elected lane issues tcgen05.mma / tcgen05.commit.
+    // GEMM layer l of a net reads its A operand from shared memory when l is even (layer 0 wrote it
+    // there) and from tensor memory when l is odd; accumulator buffers alternate chunk by chunk.
     const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
     const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
     const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
-    uint32_t stage = 0, phase = 0, a_ph = 0, e_ph = 0;
+    uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
     for (int64_t it = 0; it < iters; it++) {
       for (int net = 0; net < 2; net++) {
         if (!((P.net_mask >> net) & 1)) continue;
         const TcNet& N = P.nets[net];
         for (int l = 0; l < N.n_layers; l++) {
           const TcLayer L = N.layers[l];
+          const int src = l & 1;
           const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)L.mma_n);
           for (int j = 0; j < L.n_chunks; j++) {
-            ptx::mbar_wait(ACC_EMPTY(j), ((e_ph >> j) & 1) ^ 1, P.err, 0x200 | j);
-            e_ph ^= 1u << j;
-            const uint32_t d_tmem = tmem_base + (uint32_t)(j * NCH);
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u, P.err, 0x200 | buf);
+            acc_it++;
+            const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
             for (int c = 0; c < L.k_chunks; c++) {
               if (j == 0) {
-                ptx::mbar_wait(A_READY(c), (a_ph >> c) & 1, P.err, 0x300 | c);
-                a_ph ^= 1u << c;
+                const int b = 8 * src + c;
+                ptx::mbar_wait(A_READY(0, b), (a_ph >> b) & 1, P.err, 0x300 | b);
+                a_ph ^= 1u << b;
               }
               ptx::mbar_wait(W_FULL(stage), phase, P.err, 0x400 | stage);
               ptx::tc_fence_after();
-              const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
               const uint64_t bd = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
               if (ptx::elect_one()) {
+                if (src == 0) {
+                  const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
 #pragma unroll
-                for (int k = 0; k < KCH / 16; k++)
-                  ptx::mma_f16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+                  for (int k = 0; k < KCH / 16; k++)
+                    ptx::mma_f16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+                } else {
+                  const uint32_t at = tmem_base + TM_A + (uint32_t)(c * (KCH / 2));
+#pragma unroll
+                  for (int k = 0; k < KCH / 16; k++)
+                    ptx::mma_f16_ts(d_tmem, at + 8 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+                }
                 if (CLUSTER > 1) ptx::mma_commit_multicast(W_EMPTY(stage), CMASK);
                 else ptx::mma_commit(W_EMPTY(stage));
-                if (c == L.k_chunks - 1) ptx::mma_commit(ACC_FULL(j));
+                if (c == L.k_chunks - 1) ptx::mma_commit(ACC_FULL(buf));
               }
               __syncwarp();
               if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
@@ -237,7 +257,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
     const int sw = row & 7;
     const float slope = P.head.slope;
     const uint64_t slope2 = ptx::pack_f32x2(slope, slope);
-    uint32_t f_ph = 0;
+    uint32_t acc_it = 0;
     int bias_buf = 0;
 
     for (int64_t it = 0; it < iters; it++) {
@@ -253,7 +273,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
       for (int net = 0; net < 2; net++) {
         if (!((P.net_mask >> net) & 1)) continue;
         const TcNet& N = P.nets[net];
-        // ---- layer 0 on CUDA cores: K = 3 after folding the latent into table.w
+        // ---- layer 0 on CUDA cores: K = 3 after folding the latent into table.w; writes the shared-memory
+        // activations (free: their last readers, the MMAs of the previous even layer, completed before the
+        // accumulator barrier this thread passed last)
         epi_bar();  // everybody is past the previous use of sTab / sBias
         {
           const float4* t = P.tables + N.l0_table * 512;
@@ -278,23 +300,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
                          ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
           }
           ptx::fence_proxy_async_smem();
-          ptx::mbar_arrive(A_READY(c));
+          ptx::mbar_arrive(A_READY(0, c));
         }
 
         for (int l = 0; l < N.n_layers; l++) {
           const TcLayer L = N.layers[l];
-          const int last = L.n_chunks - 1;
-          ptx::mbar_wait(ACC_FULL(last), (f_ph >> last) & 1, P.err, 0x500 | l);
-          ptx::tc_fence_after();
           if (L.kind == KIND_HEAD) {
-            f_ph ^= 1u;
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l);
+            acc_it++;
+            ptx::tc_fence_after();
             uint32_t r[8];
             if (h == 0) {
-              ptx::tmem_ld8(tmem_lane, r);
+              ptx::tmem_ld8(tmem_lane + TM_ACC + buf * NCH, r);
               ptx::tmem_wait_ld();
             }
             ptx::tc_fence_before();
-            ptx::mbar_arrive(ACC_EMPTY(0));
+            ptx::mbar_arrive(ACC_EMPTY(buf));
             if (h == 0) {
               float* dst = net == 0 ? yc : yt;
 #pragma unroll
@@ -305,6 +327,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
             }
             continue;
           }
+          const int dsti = (l + 1) & 1;  // where the next layer reads its A operand: 0 shared memory, 1 tensor memory
           epi_bar();  // all epilogue warps finished the previous drain: smem tables may be rewritten
           // prefetch what the NEXT layer's drain needs
           const int next_kind = (l + 1 < N.n_layers) ? N.layers[l + 1].kind : -1;
@@ -318,30 +341,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
             pre_t1 = __ldg(t + et + 256);
           }
           const float* bias = sBias + bias_buf * 512;
-          for (int j = 0; j <= last; j++) {
-            if (j != last) ptx::mbar_wait(ACC_FULL(j), (f_ph >> j) & 1, P.err, 0x600 | j);
-            f_ph ^= 1u << j;
+          for (int j = 0; j < L.n_chunks; j++) {
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j);
+            acc_it++;
+            ptx::tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
-              const int col0 = j * NCH + half * 64 + h * 32;
+              const int col0 = j * NCH + half * 64 + h * 32;  // output column of this layer
               uint32_t r[32];
-              ptx::tmem_ld32(tmem_lane + col0, r);
+              ptx::tmem_ld32(tmem_lane + TM_ACC + buf * NCH + half * 64 + h * 32, r);
               ptx::tmem_wait_ld();
               if (half == 1) {
                 ptx::tc_fence_before();
-                ptx::mbar_arrive(ACC_EMPTY(j));
+                ptx::mbar_arrive(ACC_EMPTY(buf));
               }
               const int c = 2 * j + half;
+              uint32_t pk[16];
 #pragma unroll
               for (int gq = 0; gq < 4; gq++) {
-                uint32_t pk[4];
                 if (L.kind == KIND_HIDDEN_XYZ) {
 #pragma unroll
                   for (int f = 0; f < 8; f += 2) {
                     const float4 t0 = sTab[col0 + gq * 8 + f], t1 = sTab[col0 + gq * 8 + f + 1];
                     const float v0 = leaky(__uint_as_float(r[gq * 8 + f]) + fmaf(t0.x, x, fmaf(t0.y, y, fmaf(t0.z, z, t0.w))), slope);
                     const float v1 = leaky(__uint_as_float(r[gq * 8 + f + 1]) + fmaf(t1.x, x, fmaf(t1.y, y, fmaf(t1.z, z, t1.w))), slope);
-                    pk[f >> 1] = ptx::pack_bf16x2(v0, v1);
+                    pk[gq * 4 + (f >> 1)] = ptx::pack_bf16x2(v0, v1);
                   }
                 } else {
                   const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
@@ -353,13 +378,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
                     const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
                     const uint64_t t = ptx::add_f32x2(acc, bb[f]);       // FADD2
                     const uint64_t u = ptx::mul_f32x2(t, slope2);        // FMUL2
-                    pk[f] = ptx::pack_bf16x2(fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u)), fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u)));
+                    pk[gq * 4 + f] = ptx::pack_bf16x2(fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u)), fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u)));
                   }
                 }
-                st_shared_v4(a_row + c * A_CHUNK_BYTES + (((4 * h + gq) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+                if (dsti == 0)
+                  st_shared_v4(a_row + c * A_CHUNK_BYTES + (((4 * h + gq) ^ sw) << 4), pk[gq * 4], pk[gq * 4 + 1],
+                               pk[gq * 4 + 2], pk[gq * 4 + 3]);
               }
-              ptx::fence_proxy_async_smem();
-              ptx::mbar_arrive(A_READY(c));
+              if (dsti == 0) {
+                ptx::fence_proxy_async_smem();
+              } else {
+                // bf16 pair (k, k+1) of row m -> TMEM lane m, column k/2: the layout tcgen05.mma reads A in
+                ptx::tmem_st16(tmem_lane + TM_A + (uint32_t)(c * (KCH / 2) + h * 16), pk);
+                ptx::tmem_wait_st();
+                ptx::tc_fence_before();
+              }
+              ptx::mbar_arrive(A_READY(0, 8 * dsti + c));
             }
           }
           // publish the prefetched tables for the next drain (made visible by its epi_bar)

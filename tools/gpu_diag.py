@@ -29,7 +29,7 @@ def stage_probe():
         A = rng.standard_normal((128, K)).astype(np.float32)
         W = rng.standard_normal((128, K)).astype(np.float32)
         ref = bf16_round(A).astype(np.float64) @ bf16_round(W).astype(np.float64).T
-        for bulk in (0, 1):
+        for bulk in (0, 1, 3):
             D = np.zeros((128, 128), np.float32)
             rc = L.dj_debug_umma_probe(A.ctypes.data, W.ctypes.data, K, bulk, 0, 0, 0, D.ctypes.data)
             key = "K%d_bulk%d" % (K, bulk)
