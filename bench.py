@@ -140,6 +140,7 @@ def main():
     ap.add_argument("--use-net", type=int, default=1)
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--query-only", action="store_true", help="diagnostics: time the grid query alone (not a bench line)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -180,6 +181,10 @@ def main():
         vol = R.decode_shape_device(code_dev, dec, dims, use_net=u, padding=0.1, sigmoid=False)
         if ev:
             ev[1].record()
+        if args.query_only:
+            if ev:
+                ev[2].record()
+            return vol, vol
         v, f = R.marching_cubes(vol.reshape(dims), 0.0, "ascent")
         if ev:
             ev[2].record()
@@ -208,6 +213,11 @@ def main():
     mc_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     nv, nf = int(v.shape[0]), int(f.shape[0])
 
+    if args.query_only:
+        if rank == 0:
+            print(json.dumps({"diagnostic": "query-only", "grid_query_ms": q_ms, "queries_per_s": npts / (q_ms * 1e-3),
+                              "tflops_alg": npts * FLOP_ALG[u] / (q_ms * 1e-3) / 1e12, "clocks": sampler.stop()}))
+        return
     # ---- end to end through the public API: host code in, host mesh out
     for _ in range(2):
         mesh = R.create_mesh(code, dec, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)

@@ -3,6 +3,7 @@
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
+#include "mlp_tc2.cuh"
 #include "mc.cuh"
 #include "sampler.cuh"
 #include "debug_probe.cuh"
@@ -24,13 +25,18 @@ struct DjPack {
   uint8_t* stream[2] = {nullptr, nullptr};
   float* bias_dev = nullptr;
   tc::TcNet nets[2];
+  // CTA-pair (cta_group::2) program: one weight stream per cluster rank
+  uint8_t* stream2[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  tc2::Net nets2[2];
+  unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
+  int tc_kernel = 2;  // 2: CTA-pair kernel (default); 1: single-CTA kernel (env DEEPJOIN_B200_TC=1)
   // per-call shape constants + device error word
   float4* tables = nullptr;
   unsigned int* err = nullptr;
   simt::FoldParams fold{};
   // workspaces (grow only)
   DevBuf ws_fwd, ws_lat, ws_host, ws_vol;
-  bool tc_attr_set = false;
+  bool tc_attr_set = false, tc_attr_set2 = false;
   int tc_cluster = 2;  // CTAs sharing one weight stream (1, 2 or 4); env DEEPJOIN_B200_CLUSTER
 };
 
@@ -41,11 +47,15 @@ static void free_pack(DjPack* p) {
     for (float* q : *v)
       if (q) cudaFree(q);
   if (p->fWx) cudaFree(p->fWx);
-  for (int i = 0; i < 2; i++)
+  for (int i = 0; i < 2; i++) {
     if (p->stream[i]) cudaFree(p->stream[i]);
+    for (int r = 0; r < 2; r++)
+      if (p->stream2[i][r]) cudaFree(p->stream2[i][r]);
+  }
   if (p->bias_dev) cudaFree(p->bias_dev);
   if (p->tables) cudaFree(p->tables);
   if (p->err) cudaFree(p->err);
+  if (p->prof) cudaFree(p->prof);
   p->ws_fwd.release();
   p->ws_lat.release();
   p->ws_host.release();
@@ -101,6 +111,10 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     const int c = atoi(e);
     if (c == 1 || c == 2 || c == 4) p->tc_cluster = c;
   }
+  if (const char* e = getenv("DEEPJOIN_B200_TC")) {
+    const int c = atoi(e);
+    if (c == 1 || c == 2) p->tc_kernel = c;
+  }
   p->L = L; p->Lb = Lb; p->H = H; p->K3 = K3;
   auto bail = [&](int code) { free_pack(p); return code; };
 
@@ -149,6 +163,8 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
   DJ_TRY(cudaMalloc((void**)&p->tables, 3 * 512 * sizeof(float4)));
   DJ_TRY(cudaMalloc((void**)&p->err, sizeof(unsigned int)));
   DJ_TRY(cudaMemset(p->err, 0, sizeof(unsigned int)));
+  DJ_TRY(cudaMalloc((void**)&p->prof, (size_t)prop.multiProcessorCount * 16 * sizeof(unsigned long long)));
+  DJ_TRY(cudaMemset(p->prof, 0, (size_t)prop.multiProcessorCount * 16 * sizeof(unsigned long long)));
 
   // ---- tensor-core program + weight stream
   std::vector<float> bias_host;
@@ -194,6 +210,52 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     DJ_TRY(cudaMalloc((void**)&p->stream[net], blob.size()));
     DJ_TRY(cudaMemcpy(p->stream[net], blob.data(), blob.size(), cudaMemcpyHostToDevice));
     N.stream = p->stream[net];
+  }
+  // ---- CTA-pair program: same layers / bias offsets; every 128-row output chunk is split 64/64 between the
+  // two CTAs of a pair and a ring stage carries K = 128 (two [rows x 64] tiles)
+  for (int net = 0; net < 2; net++) {
+    const int nl = net == 0 ? d->f_layers : d->h_layers;
+    const float* const* W = net == 0 ? f_w : h_w;
+    const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
+    const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
+    const tc::TcNet& N1 = p->nets[net];
+    tc2::Net& N = p->nets2[net];
+    memset(&N, 0, sizeof N);
+    N.n_layers = N1.n_layers;
+    N.l0_table = N1.l0_table;
+    N.head_leaky = N1.head_leaky;
+    std::vector<uint8_t> blob[2];
+    for (int l = 1; l < nl; l++) {
+      const tc::TcLayer& T1 = N1.layers[l - 1];
+      tc2::Layer& T = N.layers[l - 1];
+      const bool head = (l == nl - 1);
+      const bool reinj = (net == 0 && l == li);
+      const int n_real = outs[l];
+      const int k_real = reinj ? K3 : ins[l];
+      if (T1.k_chunks % 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K chunks must be even", l));
+      T.n_chunks = T1.n_chunks;
+      T.k_stages = (int16_t)(T1.k_chunks / 2);
+      T.mma_n = (int16_t)(head ? 32 : 128);
+      T.kind = T1.kind;
+      T.bias_off = T1.bias_off;
+      T.table = T1.table;
+      const int rows = T.mma_n / 2;  // weight rows per CTA and tile
+      T.tile_bytes = rows * 128;
+      T.stage_bytes = 2 * T.tile_bytes;
+      for (int j = 0; j < T.n_chunks; j++)
+        for (int st = 0; st < T.k_stages; st++)
+          for (int r = 0; r < 2; r++)
+            for (int kc = 0; kc < 2; kc++) {
+              const size_t o = blob[r].size();
+              blob[r].resize(o + T.tile_bytes);
+              pack_tile(W[l], ins[l], n_real, k_real, j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blob[r].data() + o);
+            }
+    }
+    for (int r = 0; r < 2; r++) {
+      DJ_TRY(cudaMalloc((void**)&p->stream2[net][r], blob[r].size()));
+      DJ_TRY(cudaMemcpy(p->stream2[net][r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
+      N.stream[r] = p->stream2[net][r];
+    }
   }
   DJ_TRY(upload(bias_host.data(), bias_host.size(), &p->bias_dev));
 #undef DJ_TRY
@@ -282,6 +344,35 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
   if (n <= 0) return DJ_OK;
   int rc;
   if ((rc = launch_fold(p, code_dev, st))) return rc;
+  if (precision == DJ_PREC_BF16 && p->tc_kernel == 2) {
+    tc2::Params P;
+    memset(&P, 0, sizeof P);
+    P.nets[0] = p->nets2[0];
+    P.nets[1] = p->nets2[1];
+    P.net_mask = net_mask;
+    P.grid_mode = G.on;
+    if (const char* e = getenv("DEEPJOIN_B200_DEBUG")) P.debug = atoi(e);
+    P.bias = p->bias_dev;
+    P.tables = p->tables;
+    P.xyz = xyz_dev;
+    P.n = n;
+    P.d0 = G.d0; P.d1 = G.d1; P.d2 = G.d2;
+    P.step0 = G.step(G.d0); P.step1 = G.step(G.d1); P.step2 = G.step(G.d2);
+    P.stop = G.stop; P.offs = G.offs; P.r_lo = G.r_lo;
+    P.head = head;
+    P.out = out_dev;
+    P.err = p->err;
+    P.prof = p->prof;
+    const int64_t ntiles = (n + tc2::TILE_M - 1) / tc2::TILE_M;
+    const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);  // whole CTA pairs
+    if (!p->tc_attr_set2) {
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      p->tc_attr_set2 = true;
+    }
+    tc2::tc2_forward_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    DJ_LAUNCHED();
+    return DJ_OK;
+  }
   if (precision == DJ_PREC_BF16) {
     tc::TcParams P;
     memset(&P, 0, sizeof P);
@@ -289,6 +380,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     P.nets[1] = p->nets[1];
     P.net_mask = net_mask;
     P.grid_mode = G.on;
+    if (const char* e = getenv("DEEPJOIN_B200_DEBUG")) P.debug = atoi(e);
     P.bias = p->bias_dev;
     P.tables = p->tables;
     P.xyz = xyz_dev;
@@ -738,6 +830,14 @@ extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* fa
 // ====================================================================== debug probe (not product path)
 // A_host [128,K], W_host [128,K] fp32 (nn.Linear layout); D_host [128,128] = bf16(A) . bf16(W)^T.
 // desc_tmpl == 0 / k_adv_bytes == 0 / idesc == 0 select the encodings the product kernel uses.
+extern "C" int dj_debug_read_prof(DjPack* p, unsigned long long* out_host, int n_words) {
+  if (!p || !out_host || n_words < 0 || n_words > p->num_sms * 16) return fail(DJ_ERR_INVALID, "dj_debug_read_prof: bad argument");
+  DeviceGuard g(p->device);
+  DJ_CUDA(cudaDeviceSynchronize());
+  DJ_CUDA(cudaMemcpy(out_host, p->prof, (size_t)n_words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return DJ_OK;
+}
+
 extern "C" int dj_debug_umma_probe(const float* A_host, const float* W_host, int K, int use_bulk, int k_adv_bytes,
                                    uint32_t idesc, uint64_t desc_tmpl, float* D_host) {
   if (!A_host || !W_host || !D_host || K < 64 || K > 256 || K % 64) return fail(DJ_ERR_INVALID, "dj_debug_umma_probe: bad argument");

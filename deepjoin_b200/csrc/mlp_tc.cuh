@@ -71,6 +71,7 @@ struct TcParams {
   TcNet nets[2];
   int32_t net_mask;
   int32_t grid_mode;
+  int32_t debug;         // bench diagnostics only (DEEPJOIN_B200_DEBUG): 1 = do not re-stream weights, 2 = skip the MMAs
   const float* bias;
   const float4* tables;  // [3][512] (wx, wy, wz, c) per-shape constants
   const float* xyz;
@@ -177,7 +178,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
           const uint32_t part = bytes / CLUSTER;
           for (int s = 0; s < ns; s++) {
             ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage);  // every CTA of the cluster freed the slot
-            if (ptx::elect_one()) {
+            if ((P.debug & 1) && (it > 0 || net > 0 || l > 0)) {
+              if (ptx::elect_one()) ptx::mbar_arrive(W_FULL(stage));
+            } else if (ptx::elect_one()) {
               ptx::mbar_expect_tx(W_FULL(stage), bytes);
               if (CLUSTER > 1)
                 ptx::bulk_g2s_multicast(sW + stage * STAGE_BYTES + rank * part, src + rank * part, part, W_FULL(stage), CMASK);
@@ -193,54 +196,64 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_forward_kernel(const __grid_co
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    // The whole warp runs the (warp-uniform) loop so addresses / descriptors live in uniform
-    // registers; one elected lane issues tcgen05.mma / tcgen05.commit.
     // GEMM layer l of a net reads its A operand from shared memory when l is even (layer 0 wrote it
     // there) and from tensor memory when l is odd; accumulator buffers alternate chunk by chunk.
-    const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
-    const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
-    const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
-    uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
-    for (int64_t it = 0; it < iters; it++) {
-      for (int net = 0; net < 2; net++) {
-        if (!((P.net_mask >> net) & 1)) continue;
-        const TcNet& N = P.nets[net];
-        for (int l = 0; l < N.n_layers; l++) {
-          const TcLayer L = N.layers[l];
-          const int src = l & 1;
-          const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)L.mma_n);
-          for (int j = 0; j < L.n_chunks; j++) {
-            const uint32_t buf = acc_it & 1u;
-            ptx::mbar_wait(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u, P.err, 0x200 | buf);
-            acc_it++;
-            const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
-            for (int c = 0; c < L.k_chunks; c++) {
-              if (j == 0) {
-                const int b = 8 * src + c;
-                ptx::mbar_wait(A_READY(0, b), (a_ph >> b) & 1, P.err, 0x300 | b);
-                a_ph ^= 1u << b;
-              }
-              ptx::mbar_wait(W_FULL(stage), phase, P.err, 0x400 | stage);
-              ptx::tc_fence_after();
-              const uint64_t bd = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
-              if (ptx::elect_one()) {
-                if (src == 0) {
-                  const uint64_t ad = a_desc0 + (uint64_t)(c * (A_CHUNK_BYTES >> 4));
-#pragma unroll
-                  for (int k = 0; k < KCH / 16; k++)
-                    ptx::mma_f16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
-                } else {
-                  const uint32_t at = tmem_base + TM_A + (uint32_t)(c * (KCH / 2));
-#pragma unroll
-                  for (int k = 0; k < KCH / 16; k++)
-                    ptx::mma_f16_ts(d_tmem, at + 8 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+    // The whole warp walks the (warp-uniform) issue program so that addresses and descriptors can live
+    // in uniform registers; one elected lane issues tcgen05.mma / tcgen05.commit.  The per-stage path - a barrier
+    // poll, four MMAs, one commit - must stay well under the 256 tensor-pipe cycles a stage is worth:
+    // no out-of-line calls here.
+    {
+      const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
+      const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
+      const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
+      uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
+      for (int64_t it = 0; it < iters; it++) {
+        for (int net = 0; net < 2; net++) {
+          if (!((P.net_mask >> net) & 1)) continue;
+          const TcNet& N = P.nets[net];
+          const int nl = N.n_layers;
+          for (int l = 0; l < nl; l++) {
+            const int n_chunks = N.layers[l].n_chunks, k_chunks = N.layers[l].k_chunks;
+            const uint32_t idesc = ptx::umma_idesc_bf16(128, (uint32_t)N.layers[l].mma_n);
+            const int src = l & 1;
+            for (int j = 0; j < n_chunks; j++) {
+              const uint32_t buf = acc_it & 1u;
+              ptx::mbar_spin(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u);
+              acc_it++;
+              const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
+              uint64_t ad = a_desc0;
+              uint32_t at = tmem_base + TM_A;
+              uint32_t ab = A_READY(0, 8 * src);
+#pragma unroll 1
+              for (int c = 0; c < k_chunks; c++) {
+                if (j == 0) {
+                  ptx::mbar_spin(ab, (a_ph >> (8 * src + c)) & 1u);
+                  ab += 8;
                 }
-                if (CLUSTER > 1) ptx::mma_commit_multicast(W_EMPTY(stage), CMASK);
-                else ptx::mma_commit(W_EMPTY(stage));
-                if (c == L.k_chunks - 1) ptx::mma_commit(ACC_FULL(buf));
+                ptx::mbar_spin(W_FULL(stage), phase);
+                ptx::tc_fence_after();
+                const uint64_t bd = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+                if (ptx::elect_one()) {
+                  if (P.debug & 2) {
+                  } else if (src == 0) {
+#pragma unroll
+                    for (int k = 0; k < KCH / 16; k++)
+                      ptx::mma_f16_ss(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < KCH / 16; k++)
+                      ptx::mma_f16_ts(d_tmem, at + 8 * k, bd + 2 * k, idesc, (uint32_t)((c | k) != 0));
+                  }
+                  if (CLUSTER > 1) ptx::mma_commit_multicast(W_EMPTY(stage), CMASK);
+                  else ptx::mma_commit(W_EMPTY(stage));
+                  if (c == k_chunks - 1) ptx::mma_commit(ACC_FULL(buf));
+                }
+                __syncwarp();
+                ad += A_CHUNK_BYTES >> 4;
+                at += KCH / 2;
+                if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
               }
-              __syncwarp();
-              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+              if (j == 0) a_ph ^= ((1u << k_chunks) - 1u) << (8 * src);
             }
           }
         }

@@ -1,0 +1,452 @@
+// Fused persistent decoder forward on tcgen05 tensor cores, CTA-pair edition (sm_100a, cta_group::2).
+//
+// replaces: Decoder.forward  (networks/decoder_z_lb_both_leaky_n_sdf.py:174-457) for one latent
+// code shared by all rows, i.e. what decode_samples (core/reconstruct.py:115-129) feeds it.
+//
+// Same dataflow as mlp_tc.cuh (activations ping-pong between shared memory and tensor memory, two
+// accumulator buffers, latent folded into per-shape constants) but the two CTAs of a cluster (one TPC)
+// run ONE 256 x 128 x 16 tcgen05.mma.cta_group::2 stream: each CTA keeps its own 128 query points
+// (A operand and accumulators in its own shared / tensor memory) and only HALF of every weight tile
+// (64 of the 128 output rows), so
+//   * each weight byte is fetched from L2 once per 256 points instead of once per 128,
+//   * the tensor core reads half as many B bytes from shared memory per MMA,
+//   * one 16 KB ring stage per CTA now carries K = 128, i.e. 8 MMAs / 512 tensor-pipe cycles per trip of
+//     the issue loop, which hides the loop's own latency (barrier polls, descriptor set-up).
+// Only the leader CTA (cluster rank 0) issues MMAs; completion is multicast to both CTAs' barriers
+// (tcgen05.commit ... multicast::cluster); the peer's epilogue warps arrive on the leader's barriers
+// through mapa / mbarrier.arrive.release.cluster, and the peer's idle MMA warp relays "my half of the
+// weight stage has landed" to the leader.
+//
+// Warp roles (320 threads per CTA): warp 0 = weight producer (TMA engine, 1-D bulk copies),
+// warp 1 = MMA issuer (leader) / weight-barrier relay (peer) + TMEM allocation, warps 2..9 = epilogue
+// (TMEM lane quarter = warp % 4; warps 2-5 drain columns [0,64) of every 128-column accumulator chunk,
+// warps 6-9 columns [64,128)).
+#pragma once
+#include <type_traits>
+#include "mlp_tc.cuh"
+
+namespace dj {
+namespace tc2 {
+
+using tc::KIND_HEAD;
+using tc::KIND_HIDDEN;
+using tc::KIND_HIDDEN_XYZ;
+
+constexpr int TILE_M = 128;                      // query points per CTA (256 per CTA pair)
+constexpr int KCH = 64;                          // k-chunk: 64 bf16 = one 128 B swizzle row
+constexpr int NCH = 128;                         // accumulator chunk (TMEM columns)
+constexpr int A_CHUNK_BYTES = TILE_M * KCH * 2;  // 16 KB
+constexpr int STAGE_BYTES = 16384;               // per CTA: two [64 x 64] bf16 tiles = K 128 of its 64 weight rows
+constexpr int NSTAGES = 5;
+constexpr int MAX_LAYERS = 10;
+constexpr int NEPI = 256;
+constexpr int NTHREADS = 64 + NEPI;
+constexpr int EPI_WARPS = NEPI / 32;
+
+constexpr int SM_A = 0;
+constexpr int SM_W = SM_A + 8 * A_CHUNK_BYTES;
+constexpr int SM_BIAS = SM_W + NSTAGES * STAGE_BYTES;
+constexpr int SM_TAB = SM_BIAS + 2 * 512 * 4;
+constexpr int SM_BAR = SM_TAB + 512 * 16;
+constexpr int SM_END = SM_BAR + 256;
+constexpr int SMEM_BYTES = SM_END + 1024;  // slack for 1024-B alignment
+
+constexpr uint32_t TM_A = 0;      // TMEM columns [0,256): bf16 activations (A operand of odd layers)
+constexpr uint32_t TM_ACC = 256;  // TMEM columns [256,512): two fp32 accumulator buffers
+
+struct Layer {
+  int16_t n_chunks;   // 128-column accumulator chunks of this layer
+  int16_t k_stages;   // ring stages per chunk (K / 128)
+  int16_t mma_n;      // N of each MMA over the pair (128 hidden, 32 head)
+  int16_t kind;
+  int32_t bias_off;   // float offset into Params::bias (KIND_HIDDEN / KIND_HEAD)
+  int32_t table;      // xyzw table id (KIND_HIDDEN_XYZ)
+  int32_t stage_bytes;  // per CTA
+  int32_t tile_bytes;   // one [mma_n/2 x 64] tile
+};
+struct Net {
+  int32_t n_layers;
+  int32_t l0_table;
+  int32_t head_leaky;
+  int32_t pad;
+  const uint8_t* stream[2];  // per cluster rank
+  Layer layers[MAX_LAYERS];
+};
+struct Params {
+  Net nets[2];
+  int32_t net_mask;
+  int32_t grid_mode;
+  int32_t debug;  // bench diagnostics only (DEEPJOIN_B200_DEBUG): 1 = do not re-stream weights, 2 = skip the MMAs
+  int32_t pad1;
+  const float* bias;
+  const float4* tables;  // [3][512] (wx, wy, wz, c) per-shape constants
+  const float* xyz;
+  int64_t n;
+  int32_t d0, d1, d2, pad0;
+  double step0, step1, step2, stop, offs;
+  int64_t r_lo;
+  HeadCfg head;
+  float* out;
+  unsigned int* err;
+  unsigned long long* prof;  // [gridDim.x][16] cycle counters, filled when debug & 8 (tools/gpu_diag.py prof)
+};
+
+__device__ __forceinline__ void grid_point(const Params& P, int64_t r, float& x, float& y, float& z) {
+  int k = (int)(r % P.d2);
+  int64_t q = r / P.d2;
+  int j = (int)(q % P.d0);
+  int i = (int)(q / P.d0);
+  x = tc::lin_axis(j, P.d0, P.step0, P.stop, P.offs);
+  y = tc::lin_axis(i, P.d1, P.step1, P.stop, P.offs);
+  z = tc::lin_axis(k, P.d2, P.step2, P.stop, P.offs);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_forward_kernel(const __grid_constant__ Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t sA = base + SM_A, sW = base + SM_W;
+  float* sBias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float4* sTab = reinterpret_cast<float4*>(smem + SM_TAB);
+  const uint32_t bar0 = base + SM_BAR;
+  auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGES + s); };
+  // A_READY(b, j): K range [128 j, 128 j + 128) of the activations in buffer b (0 shared memory, 1 tensor
+  // memory) is published by BOTH CTAs (leader's barrier; 2 x 8 warp arrivals)
+  auto A_READY = [&](int b, int j) { return bar0 + 8u * (2 * NSTAGES + 4 * b + j); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * NSTAGES + 8 + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * NSTAGES + 10 + i); };  // leader's barrier, 2 x 8 arrivals
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 12));
+  static_assert(8 * (2 * NSTAGES + 12) + 4 <= 256, "barrier block");
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+  // both CTAs of a pair (and, for simplicity, all pairs) run the same number of passes; passes beyond
+  // the last tile compute on zeros and write nothing
+  const int64_t iters = (ntiles + gridDim.x - 1) / gridDim.x;
+  const bool prof = (P.debug & 8) != 0;
+  auto tick = [&]() -> long long { return prof ? clock64() : 0ll; };
+  unsigned long long* pc = P.prof + (size_t)blockIdx.x * 16;
+  long long w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  const long long t_begin = tick();
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGES; s++) {
+      ptx::mbar_init(W_FULL(s), rank == 0 ? 2 : 1);  // leader: own copy + the peer's relay
+      ptx::mbar_init(W_EMPTY(s), 1);
+    }
+    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(0, c), 2 * EPI_WARPS);
+    for (int i = 0; i < 2; i++) {
+      ptx::mbar_init(ACC_FULL(i), 1);
+      ptx::mbar_init(ACC_EMPTY(i), 2 * EPI_WARPS);
+    }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(ptx::smem_u32((const void*)tmem_slot), 512);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // the peer's barriers are initialised before anything is signalled to them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer: this CTA's half of every stage =====================
+    uint32_t stage = 0, phase = 0;
+    for (int64_t it = 0; it < iters; it++) {
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const Net& N = P.nets[net];
+        const uint8_t* src = N.stream[rank];
+        for (int l = 0; l < N.n_layers; l++) {
+          const int ns = N.layers[l].n_chunks * N.layers[l].k_stages;
+          const uint32_t bytes = (uint32_t)N.layers[l].stage_bytes;
+          for (int s = 0; s < ns; s++) {
+            { const long long t = tick(); ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage); w0 += tick() - t; }
+            if ((P.debug & 1) && (it > 0 || net > 0 || l > 0)) {
+              if (ptx::elect_one()) ptx::mbar_arrive(W_FULL(stage));
+            } else if (ptx::elect_one()) {
+              ptx::mbar_expect_tx(W_FULL(stage), bytes);
+              ptx::bulk_g2s(sW + stage * STAGE_BYTES, src, bytes, W_FULL(stage));
+            }
+            __syncwarp();
+            src += bytes;
+            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+    if (prof && lane == 0) { pc[9] = tick() - t_begin; pc[10] = w0; }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer: relay "my half of the stage has landed" to the leader =====================
+    int per_pass = 0;
+    for (int net = 0; net < 2; net++) {
+      if (!((P.net_mask >> net) & 1)) continue;
+      for (int l = 0; l < P.nets[net].n_layers; l++) per_pass += P.nets[net].layers[l].n_chunks * P.nets[net].layers[l].k_stages;
+    }
+    const uint32_t lead_full0 = ptx::mapa(W_FULL(0), 0);
+    uint32_t stage = 0, phase = 0;
+    for (int64_t i = 0; i < iters * per_pass; i++) {
+      { const long long t = tick(); ptx::mbar_spin(W_FULL(stage), phase); w0 += tick() - t; }
+      if (ptx::elect_one()) ptx::mbar_arrive_cluster(lead_full0 + 8u * stage);
+      __syncwarp();
+      if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+    }
+    if (prof && lane == 0) { pc[11] = tick() - t_begin; pc[12] = w0; }
+  } else if (warp == 1) {
+    // ===================== leader: MMA issuer for the pair =====================
+    // The whole warp walks the (warp-uniform) issue program; one elected lane issues tcgen05.mma /
+    // tcgen05.commit.  GEMM layer l of a net reads its A operand from shared memory when l is even
+    // (layer 0 wrote it there) and from tensor memory when l is odd; accumulator buffers alternate.
+    const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
+    const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
+    const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
+    uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
+    for (int64_t it = 0; it < iters; it++) {
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const Net& N = P.nets[net];
+        const int nl = N.n_layers;
+        for (int l = 0; l < nl; l++) {
+          const int n_chunks = N.layers[l].n_chunks, k_stages = N.layers[l].k_stages;
+          const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)N.layers[l].mma_n);
+          const uint32_t tile16 = (uint32_t)N.layers[l].tile_bytes >> 4;
+          const int src = l & 1;
+          for (int j = 0; j < n_chunks; j++) {
+            const uint32_t buf = acc_it & 1u;
+            { const long long t = tick(); ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u); w1 += tick() - t; }
+            acc_it++;
+            const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
+            uint64_t ad = a_desc0;
+            uint32_t at = tmem_base + TM_A;
+#pragma unroll 1
+            for (int s = 0; s < k_stages; s++) {
+              if (j == 0) { const long long t = tick(); ptx::mbar_spin_cluster(A_READY(src, s), (a_ph >> (4 * src + s)) & 1u); w2 += tick() - t; }
+              { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(stage), phase); w3 += tick() - t; }
+              ptx::tc_fence_after();
+              const uint64_t bd = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+              if (ptx::elect_one()) {
+                if (P.debug & 2) {
+                } else if (src == 0) {
+#pragma unroll
+                  for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                    for (int k = 0; k < KCH / 16; k++)
+                      ptx::mma2_f16_ss(d_tmem, ad + (uint64_t)(kc * (A_CHUNK_BYTES >> 4) + 2 * k), bd + (uint64_t)(kc * tile16 + 2 * k),
+                                       idesc, (uint32_t)((s | kc | k) != 0));
+                } else {
+#pragma unroll
+                  for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                    for (int k = 0; k < KCH / 16; k++)
+                      ptx::mma2_f16_ts(d_tmem, at + (uint32_t)(kc * (KCH / 2) + 8 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
+                                       (uint32_t)((s | kc | k) != 0));
+                }
+                ptx::mma2_commit(W_EMPTY(stage), 3);
+                if (s == k_stages - 1) ptx::mma2_commit(ACC_FULL(buf), 3);
+              }
+              __syncwarp();
+              ad += 2 * (A_CHUNK_BYTES >> 4);
+              at += KCH;
+              if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            }
+            if (j == 0) a_ph ^= ((1u << k_stages) - 1u) << (4 * src);
+          }
+        }
+      }
+    }
+    if (prof && lane == 0) { pc[0] = tick() - t_begin; pc[1] = w1; pc[2] = w2; pc[3] = w3; }
+  } else {
+    // ===================== epilogue: 8 warps; thread = (row, 64-column half of the chunk) ==========
+    const int q = warp & 3;              // TMEM lane quarter this warp may access
+    const int h = (warp - 2) >> 2;       // columns [64 h, 64 h + 64) of every 128-column chunk
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;     // 0..255 among epilogue threads
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_row = sA + row * 128;
+    const int sw = row & 7;
+    const float slope = P.head.slope;
+    const uint64_t slope2 = ptx::pack_f32x2(slope, slope);
+    const uint32_t lead_aready0 = ptx::mapa(A_READY(0, 0), 0);
+    const uint32_t lead_accempty0 = ptx::mapa(ACC_EMPTY(0), 0);
+    uint32_t acc_it = 0;
+    int bias_buf = 0;
+
+    for (int64_t it = 0; it < iters; it++) {
+      const int64_t tile = it * gridDim.x + blockIdx.x;
+      const int64_t g = tile * TILE_M + row;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (g < P.n) {
+        if (P.grid_mode) grid_point(P, P.r_lo + g, x, y, z);
+        else { x = __ldg(P.xyz + 3 * g); y = __ldg(P.xyz + 3 * g + 1); z = __ldg(P.xyz + 3 * g + 2); }
+      }
+      float yc[5] = {0, 0, 0, 0, 0}, yt[5] = {0, 0, 0, 0, 0};
+
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const Net& N = P.nets[net];
+        // ---- layer 0 on CUDA cores: K = 3 after folding the latent into table.w; writes the shared-memory
+        // activations (free: their last readers, the MMAs of the previous even layer, completed before the
+        // accumulator barrier this thread passed last)
+        const long long t_l0 = tick();
+        tc::epi_bar();  // everybody is past the previous use of sTab / sBias
+        {
+          const float4* t = P.tables + N.l0_table * 512;
+          sTab[et] = __ldg(t + et);
+          sTab[et + 256] = __ldg(t + et + 256);
+          if (N.layers[0].kind == KIND_HIDDEN)
+            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] =
+                __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[0].bias_off) + et);
+        }
+        tc::epi_bar();
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+          const int c = 2 * j + h;
+#pragma unroll
+          for (int gq = 0; gq < 8; gq++) {
+            float v[8];
+#pragma unroll
+            for (int f = 0; f < 8; f++) {
+              const float4 t = sTab[c * 64 + gq * 8 + f];
+              v[f] = tc::leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
+            }
+            tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_bf16x2(v[0], v[1]),
+                             ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * j);
+        }
+        w2 += tick() - t_l0;
+
+        for (int l = 0; l < N.n_layers; l++) {
+          const Layer L = N.layers[l];
+          if (L.kind == KIND_HEAD) {
+            const uint32_t buf = acc_it & 1u;
+            { const long long t = tick(); ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l); w3 += tick() - t; }
+            acc_it++;
+            ptx::tc_fence_after();
+            uint32_t r[8];
+            if (h == 0) {
+              ptx::tmem_ld8(tmem_lane + TM_ACC + buf * NCH, r);
+              ptx::tmem_wait_ld();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
+            if (h == 0) {
+              float* dst = net == 0 ? yc : yt;
+#pragma unroll
+              for (int i = 0; i < 5; i++) {
+                const float v = __uint_as_float(r[i]) + __ldg(P.bias + L.bias_off + i);
+                dst[i] = N.head_leaky ? tc::leaky(v, slope) : v;
+              }
+            }
+            continue;
+          }
+          const int dsti = (l + 1) & 1;  // where the next layer reads its A operand: 0 shared memory, 1 tensor memory
+          { const long long t = tick(); tc::epi_bar(); w1 += tick() - t; }  // all epilogue warps finished the previous drain: smem tables may be rewritten
+          // prefetch what the NEXT layer's drain needs
+          const int next_kind = (l + 1 < N.n_layers) ? N.layers[l + 1].kind : -1;
+          float2 pre_b = make_float2(0.f, 0.f);
+          float4 pre_t0 = make_float4(0, 0, 0, 0), pre_t1 = pre_t0;
+          if (next_kind == KIND_HIDDEN) {
+            pre_b = __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[l + 1].bias_off) + et);
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            const float4* t = P.tables + N.layers[l + 1].table * 512;
+            pre_t0 = __ldg(t + et);
+            pre_t1 = __ldg(t + et + 256);
+          }
+          const float* bias = sBias + bias_buf * 512;
+
+          // drain of one accumulator chunk, specialised on (layer kind, destination) so that the 64 columns
+          // of a thread are straight-line code
+          auto drain = [&](auto kind_c, auto dst_c, int j) {
+            constexpr int KIND = decltype(kind_c)::value;
+            constexpr int DST = decltype(dst_c)::value;
+            const uint32_t buf = acc_it & 1u;
+            { const long long t = tick(); ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j); w0 += tick() - t; }
+            acc_it++;
+            ptx::tc_fence_after();
+            uint32_t r[64];
+            ptx::tmem_ld64(tmem_lane + TM_ACC + buf * NCH + h * 64, r);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);  // accumulator buffer is free again
+            const int col0 = j * NCH + h * 64;  // output column of this layer
+            const int c = 2 * j + h;            // 64-wide K chunk of the next layer this thread writes
+            uint32_t pk[32];
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) {
+              if (KIND == KIND_HIDDEN_XYZ) {
+#pragma unroll
+                for (int f = 0; f < 8; f += 2) {
+                  const float4 t0 = sTab[col0 + gq * 8 + f], t1 = sTab[col0 + gq * 8 + f + 1];
+                  const float v0 = tc::leaky(__uint_as_float(r[gq * 8 + f]) + fmaf(t0.x, x, fmaf(t0.y, y, fmaf(t0.z, z, t0.w))), slope);
+                  const float v1 = tc::leaky(__uint_as_float(r[gq * 8 + f + 1]) + fmaf(t1.x, x, fmaf(t1.y, y, fmaf(t1.z, z, t1.w))), slope);
+                  pk[gq * 4 + (f >> 1)] = ptx::pack_bf16x2(v0, v1);
+                }
+              } else {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8 + 4);
+                const uint64_t bb[4] = {ptx::pack_f32x2(b0.x, b0.y), ptx::pack_f32x2(b0.z, b0.w),
+                                        ptx::pack_f32x2(b1.x, b1.y), ptx::pack_f32x2(b1.z, b1.w)};
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                  const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                  const uint64_t t = ptx::add_f32x2(acc, bb[f]);       // FADD2
+                  const uint64_t u = ptx::mul_f32x2(t, slope2);        // FMUL2
+                  pk[gq * 4 + f] = ptx::pack_bf16x2(fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u)), fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u)));
+                }
+              }
+              if (DST == 0)
+                tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), pk[gq * 4], pk[gq * 4 + 1], pk[gq * 4 + 2],
+                                 pk[gq * 4 + 3]);
+            }
+            if (DST == 0) {
+              ptx::fence_proxy_async_smem();
+            } else {
+              // bf16 pair (k, k+1) of row m -> TMEM lane m, column k/2: the layout tcgen05.mma reads A in
+              ptx::tmem_st32(tmem_lane + TM_A + (uint32_t)(c * (KCH / 2)), pk);
+              ptx::tmem_wait_st();
+              ptx::tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * (4 * DST + j));
+          };
+          using I0 = std::integral_constant<int, 0>;
+          using I1 = std::integral_constant<int, 1>;
+          if (L.kind == KIND_HIDDEN_XYZ) {
+            if (dsti) for (int j = 0; j < L.n_chunks; j++) drain(I1{}, I1{}, j);
+            else for (int j = 0; j < L.n_chunks; j++) drain(I1{}, I0{}, j);
+          } else {
+            if (dsti) for (int j = 0; j < L.n_chunks; j++) drain(I0{}, I1{}, j);
+            else for (int j = 0; j < L.n_chunks; j++) drain(I0{}, I0{}, j);
+          }
+          // publish the prefetched tables for the next drain (made visible by its epi_bar)
+          if (next_kind == KIND_HIDDEN) {
+            bias_buf ^= 1;
+            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = pre_b;
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            sTab[et] = pre_t0;
+            sTab[et + 256] = pre_t1;
+          }
+        }
+      }
+      if (h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
+    }
+    if (prof && warp == 2 && lane == 0) { pc[4] = tick() - t_begin; pc[5] = w0; pc[6] = w1; pc[7] = w2; pc[8] = w3; }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();  // nobody exits (or frees tensor memory) while the peer may still use its barriers / TMEM
+  if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
+}  // namespace tc2
+}  // namespace dj

@@ -181,6 +181,10 @@ int dj_create_mesh_fetch(DjMcWork* work, double* verts_host, int32_t* faces_host
 int dj_debug_umma_probe(const float* A_host, const float* W_host, int K, int use_bulk, int k_adv_bytes,
                         uint32_t idesc, uint64_t desc_tmpl, float* D_host);
 
+/* DEBUG ONLY: per-CTA cycle counters of the last tensor-core forward launched with
+ * DEEPJOIN_B200_DEBUG & 8 ([CTA][16] words; layout in csrc/mlp_tc2.cuh). */
+int dj_debug_read_prof(DjPack* pack, unsigned long long* out_host, int n_words);
+
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t dj_launch_count(int reset);
 

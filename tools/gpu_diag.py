@@ -152,7 +152,41 @@ def stage_timing():
     return res
 
 
-STAGES = {"probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
+def stage_prof():
+    """In-kernel cycle counters of the CTA-pair forward (DEEPJOIN_B200_DEBUG |= 8): where each warp role waits."""
+    import numpy as np
+    import torch
+    from tests import util
+    from deepjoin_b200 import _lib
+    from deepjoin_b200.core import reconstruct as R
+    dbg = int(os.environ.get("DEEPJOIN_B200_DEBUG", "0")) | 8
+    os.environ["DEEPJOIN_B200_DEBUG"] = str(dbg)
+    d = int(os.environ.get("PROF_DIMS", "256"))
+    dec = util.make_decoder(0, "trained_norm", precision="bf16")
+    code = util.trained_code(0)
+    for _ in range(2):
+        R.decode_shape_device(code, dec, (d, d, d), use_net=1, padding=0.1, sigmoid=False)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    R.decode_shape_device(code, dec, (d, d, d), use_net=1, padding=0.1, sigmoid=False)
+    e1.record()
+    torch.cuda.synchronize()
+    pack = dec.pack(torch.device("cuda", 0))
+    nsm = torch.cuda.get_device_properties(0).multi_processor_count
+    buf = np.zeros((nsm, 16), np.uint64)
+    _lib.check(_lib.lib().dj_debug_read_prof(pack.handle, buf.ctypes.data, buf.size))
+    names = ["mma_total", "mma_wait_acc_empty", "mma_wait_a_ready", "mma_wait_w_full", "epi_total", "epi_wait_acc_full",
+             "epi_wait_bar", "epi_l0", "epi_wait_head", "prod_total", "prod_wait_w_empty", "relay_total", "relay_wait"]
+    lead, peer = buf[0::2].astype(np.float64), buf[1::2].astype(np.float64)
+    out = {"ms": e0.elapsed_time(e1), "debug": dbg}
+    for i, nm in enumerate(names):
+        out[nm] = {"leader_mean": float(lead[:, i].mean()), "peer_mean": float(peer[:, i].mean()),
+                   "leader_max": float(lead[:, i].max())}
+    return out
+
+
+STAGES = {"prof": stage_prof, "probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
           "timing": stage_timing}
 
 if __name__ == "__main__":
