@@ -366,10 +366,12 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     const int64_t ntiles = (n + tc2::TILE_M - 1) / tc2::TILE_M;
     const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);  // whole CTA pairs
     if (!p->tc_attr_set2) {
-      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       p->tc_attr_set2 = true;
     }
-    tc2::tc2_forward_kernel<<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    if (P.debug) tc2::tc2_forward_kernel<1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    else tc2::tc2_forward_kernel<0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     DJ_LAUNCHED();
     return DJ_OK;
   }

@@ -82,6 +82,19 @@ __device__ __forceinline__ void mbar_spin(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// non-blocking probe (its result can be consumed a loop trip later, hiding the poll latency)
+__device__ __forceinline__ uint32_t mbar_test(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+
 // ---------------------------------------------------------------- async proxy
 // generic-proxy smem writes -> visible to the async proxy (tensor core / TMA reads)
 __device__ __forceinline__ void fence_proxy_async_smem() {
