@@ -129,6 +129,20 @@ def marching_cubes(volume, level, gradient_direction="descent"):
     return verts, faces
 
 
+def merge_vertices(vertices, faces):
+    """Device-side ``Mesh.merge_vertices`` (trimesh's process=True merge, core/reconstruct.py:189):
+    CUDA tensors vertices f64 [V,3] / faces int32 [F,3] -> (merged vertices, re-indexed faces)."""
+    v = vertices.detach().to(torch.float64).contiguous().clone()
+    f = faces.detach().to(torch.int32).contiguous().clone()
+    dev = v.device
+    w = _work_for(dev.index)
+    n = ctypes.c_int64()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dj_mesh_merge_vertices(w.handle, v.data_ptr(), v.shape[0], f.data_ptr(), f.shape[0],
+                                                     ctypes.byref(n), _lib.stream_ptr()))
+    return v[:n.value], f
+
+
 def create_mesh(vec, decoder, use_net, sigmoid=True, level=0.5, gradient_direction="descent", f_out=None,
                 save_values=None, dims=(256, 256, 256), batch_size=2 ** 16, padding=0.1):
     """core/reconstruct.py:135-192: grid query -> marching cubes (spacing (1+2p)/d) -> swap
@@ -156,7 +170,13 @@ def create_mesh(vec, decoder, use_net, sigmoid=True, level=0.5, gradient_directi
     vertices = np.empty((nv.value, 3), dtype=np.float64)
     faces = np.empty((nf.value, 3), dtype=np.int32)
     _lib.check(L.dj_create_mesh_fetch(w.handle, vertices.ctypes.data, faces.ctypes.data))
-    mesh = Mesh(vertices=vertices, faces=faces)
+    # trimesh's process=True (:189): the duplicate-vertex merge already ran on the device
+    # (csrc/mesh_merge.cuh); non-finite vertices cannot come out of marching cubes on a finite grid,
+    # the check keeps the contract anyway
+    mesh = Mesh(vertices=vertices, faces=faces, process=False)
+    if len(vertices) and not np.isfinite(vertices).all():
+        mesh.remove_infinite_values()
+        mesh.merge_vertices()
     if f_out is not None:
         mesh.export(f_out)
     return mesh

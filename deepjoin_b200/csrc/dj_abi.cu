@@ -6,6 +6,7 @@
 #include "mlp_tc2.cuh"
 #include "mc.cuh"
 #include "sampler.cuh"
+#include "mesh_merge.cuh"
 #include "debug_probe.cuh"
 
 using namespace dj;
@@ -663,7 +664,8 @@ extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int
 struct DjMcWork {
   int device = 0;
   mc::Dims D{};
-  DevBuf var, counts, offs, edge, misc, verts, faces;
+  DevBuf var, counts, offs, edge, misc, verts, faces, merge;
+  double* v64 = nullptr;  // create_mesh: final float64 vertices on the device (inside verts / merge)
   int64_t nblocks = 0, nv = 0, nf = 0;
   const float* vol = nullptr;
   bool counted = false;
@@ -684,7 +686,7 @@ extern "C" int dj_mc_create(int device, DjMcWork** out) {
 extern "C" int dj_mc_destroy(DjMcWork* w) {
   if (!w) return DJ_OK;
   DeviceGuard g(w->device);
-  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces}) b->release();
+  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge}) b->release();
   delete w;
   return DJ_OK;
 }
@@ -782,6 +784,67 @@ __global__ void mesh_post_kernel(const float* __restrict__ v, double* __restrict
   out[3 * i + 2] = __dsub_rn(__dmul_rn((double)v[3 * i + 2], s2), centre);
 }
 
+// Device-side Mesh.merge_vertices (csrc/mesh_merge.cuh).  v64 [nv,3] is left untouched; when vertices
+// merged, *vout points at the compacted copy inside w->merge and faces are re-indexed in place.
+// Synchronises the stream (the caller needs the count).
+static int merge_vertices_dev(DjMcWork* w, const double* v64, int64_t nv, int32_t* faces, int64_t nf, cudaStream_t st,
+                              double** vout_p, int64_t* uniq_p) {
+  *vout_p = const_cast<double*>(v64);
+  *uniq_p = nv;
+  if (nv == 0) return DJ_OK;
+  if (nv > 0x7ffffff0ll) return fail(DJ_ERR_UNSUPPORTED, "mesh with %lld vertices", (long long)nv);
+  uint32_t tsize = 1024;
+  while ((int64_t)tsize < 2 * nv) tsize <<= 1;
+  const int64_t nsb = ceil_div(nv, (int64_t)meshmerge::SCAN_BLOCK);
+  // layout (int32 words): [table tsize][canon nv][newid nv][block sums nsb][counter][vout 3 nv doubles]
+  const size_t off_canon = (size_t)tsize, off_newid = off_canon + nv, off_bs = off_newid + nv;
+  const size_t off_cnt = (off_bs + nsb + 1) & ~(size_t)1, off_vout = off_cnt + 2;
+  DJ_CUDA(w->merge.reserve(off_vout * sizeof(int32_t) + (size_t)nv * 3 * sizeof(double)));
+  int32_t* mt = w->merge.as<int32_t>();
+  unsigned long long* cnt = reinterpret_cast<unsigned long long*>(mt + off_cnt);
+  meshmerge::fill_kernel<<<(unsigned)std::min<int64_t>(ceil_div((int64_t)tsize, (int64_t)256), 4096), 256, 0, st>>>(mt, tsize, meshmerge::EMPTY);
+  DJ_LAUNCHED();
+  DJ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(unsigned long long), st));
+  meshmerge::insert_kernel<<<(unsigned)ceil_div(nv, (int64_t)256), 256, 0, st>>>(v64, nv, mt, tsize - 1);
+  DJ_LAUNCHED();
+  meshmerge::lookup_kernel<<<(unsigned)ceil_div(nv, (int64_t)256), 256, 0, st>>>(v64, nv, mt, tsize - 1, mt + off_canon, cnt);
+  DJ_LAUNCHED();
+  unsigned long long uniq = 0;
+  DJ_CUDA(cudaMemcpyAsync(&uniq, cnt, sizeof uniq, cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaStreamSynchronize(st));
+  if ((int64_t)uniq == nv) return DJ_OK;
+  double* vout = reinterpret_cast<double*>(mt + off_vout);
+  meshmerge::block_count_kernel<<<(unsigned)nsb, meshmerge::SCAN_BLOCK, 0, st>>>(mt + off_canon, nv, mt + off_bs);
+  DJ_LAUNCHED();
+  meshmerge::scan_sums_kernel<<<1, meshmerge::SCAN_BLOCK, 0, st>>>(mt + off_bs, (int)nsb);
+  DJ_LAUNCHED();
+  meshmerge::compact_kernel<<<(unsigned)nsb, meshmerge::SCAN_BLOCK, 0, st>>>(v64, mt + off_canon, nv, mt + off_bs, mt + off_newid, vout);
+  DJ_LAUNCHED();
+  if (nf > 0) {
+    meshmerge::remap_faces_kernel<<<(unsigned)ceil_div(nf * 3, (int64_t)256), 256, 0, st>>>(faces, nf * 3, mt + off_canon, mt + off_newid);
+    DJ_LAUNCHED();
+  }
+  *vout_p = vout;
+  *uniq_p = (int64_t)uniq;
+  return DJ_OK;
+}
+
+/* replaces: trimesh's merge_vertices inside trimesh.Trimesh(process=True) (core/reconstruct.py:189). */
+extern "C" int dj_mesh_merge_vertices(DjMcWork* w, double* verts_dev, int64_t n_verts, int32_t* faces_dev, int64_t n_faces,
+                                      int64_t* n_verts_out, void* stream) {
+  if (!w || !n_verts_out || n_verts < 0 || n_faces < 0 || (n_verts && !verts_dev) || (n_faces && !faces_dev))
+    return fail(DJ_ERR_INVALID, "dj_mesh_merge_vertices: bad argument");
+  DeviceGuard g(w->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  double* vout = verts_dev;
+  int64_t uniq = n_verts;
+  int rc = merge_vertices_dev(w, verts_dev, n_verts, faces_dev, n_faces, st, &vout, &uniq);
+  if (rc) return rc;
+  if (vout != verts_dev) DJ_CUDA(cudaMemcpyAsync(verts_dev, vout, (size_t)uniq * 3 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  *n_verts_out = uniq;
+  return DJ_OK;
+}
+
 extern "C" int dj_create_mesh_count(DjPack* p, DjMcWork* w, const float* code_host, int d0, int d1, int d2, double padding,
                                     int use_net, int return_occ, int apply_sigmoid, double level, int descent, int precision,
                                     int64_t* n_verts, int64_t* n_faces) {
@@ -813,17 +876,26 @@ extern "C" int dj_create_mesh_count(DjPack* p, DjMcWork* w, const float* code_ho
   w->spacing[1] = (1 + (padding * 2)) / d1;
   w->spacing[2] = (1 + (padding * 2)) / d2;
   w->centre = 0.5 + padding;
+  // world-space float64 vertices, then the duplicate-vertex merge trimesh's process=True performs (:189)
+  const int64_t nv = w->nv;
+  double* v64 = reinterpret_cast<double*>(w->verts.as<float>() + (((size_t)nv * 3 + 1) & ~(size_t)1));
+  mesh_post_kernel<<<ceil_div(nv, 256), 256, 0, st>>>(w->verts.as<float>(), v64, nv, w->spacing[0], w->spacing[1], w->spacing[2], w->centre);
+  DJ_LAUNCHED();
+  w->v64 = v64;
+  int64_t uniq = nv;
+  double* vfinal = v64;
+  if ((rc = merge_vertices_dev(w, v64, nv, w->faces.as<int>(), w->nf, st, &vfinal, &uniq))) return rc;
+  w->v64 = vfinal;
+  w->nv = uniq;
+  *n_verts = uniq;
   return DJ_OK;
 }
 
 extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* faces_host) {
-  if (!w || !w->counted || !verts_host || !faces_host) return fail(DJ_ERR_INVALID, "dj_create_mesh_fetch: bad argument");
+  if (!w || !w->counted || !w->v64 || !verts_host || !faces_host) return fail(DJ_ERR_INVALID, "dj_create_mesh_fetch: bad argument");
   DeviceGuard g(w->device);
   cudaStream_t st = 0;
-  double* v64 = reinterpret_cast<double*>(w->verts.as<float>() + (((size_t)w->nv * 3 + 1) & ~(size_t)1));
-  mesh_post_kernel<<<ceil_div(w->nv, 256), 256, 0, st>>>(w->verts.as<float>(), v64, w->nv, w->spacing[0], w->spacing[1], w->spacing[2], w->centre);
-  DJ_LAUNCHED();
-  DJ_CUDA(cudaMemcpyAsync(verts_host, v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaMemcpyAsync(verts_host, w->v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaMemcpyAsync(faces_host, w->faces.as<int>(), (size_t)w->nf * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaStreamSynchronize(st));
   return DJ_OK;

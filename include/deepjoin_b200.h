@@ -175,6 +175,13 @@ int dj_create_mesh_count(DjPack* pack, DjMcWork* work, const float* code_host, i
                          int descent, int precision, int64_t* n_verts, int64_t* n_faces);
 int dj_create_mesh_fetch(DjMcWork* work, double* verts_host, int32_t* faces_host);
 
+/* replaces: the duplicate-vertex merge of trimesh.Trimesh(vertices, faces) (default process=True,
+ * core/reconstruct.py:189): vertices whose coordinates agree after rounding to 8 decimals collapse onto
+ * the one with the smallest index, survivors keep their order, faces are re-indexed.  In place on
+ * device arrays (verts float64 [n_verts,3], faces int32 [n_faces,3]); synchronises the stream. */
+int dj_mesh_merge_vertices(DjMcWork* work, double* verts_dev, int64_t n_verts, int32_t* faces_dev, int64_t n_faces,
+                           int64_t* n_verts_out, void* stream);
+
 /* DEBUG ONLY (tools/gpu_diag.py): one 128x128xK bf16 UMMA built from the product kernel's pieces;
  * D_host [128,128] = bf16(A_host [128,K]) . bf16(W_host [128,K])^T.  Zero for k_adv_bytes / idesc /
  * desc_tmpl selects the product encodings. */

@@ -67,3 +67,24 @@ def test_full_size_256_mesh_is_consistent():
     from deepjoin_b200.mesh import Mesh
     ref = Mesh(vo, fo)
     assert np.array_equal(mesh.faces, ref.faces) and np.array_equal(mesh.vertices, ref.vertices)
+
+
+@pytest.mark.parametrize("nv,dup_frac", [(1, 0.0), (1000, 0.0), (5000, 0.3), (200000, 0.05), (3000, 1.0)])
+def test_device_vertex_merge_equals_host_merge(nv, dup_frac):
+    """csrc/mesh_merge.cuh against Mesh.merge_vertices (np.round(.., 8) + first-occurrence order)."""
+    from deepjoin_b200.core import reconstruct as R
+    from deepjoin_b200.mesh import Mesh
+    rng = np.random.default_rng(nv)
+    v = rng.uniform(-0.6, 0.6, (nv, 3))
+    ndup = int(nv * dup_frac)
+    if ndup:
+        src = rng.integers(0, nv, ndup)
+        dst = rng.integers(0, nv, ndup)
+        v[dst] = v[src] + rng.uniform(-4e-9, 4e-9, (ndup, 3))  # mostly the same key after rounding, sometimes not
+    if dup_frac == 1.0:
+        v[:] = v[0]
+    f = rng.integers(0, nv, (2 * nv + 1, 3)).astype(np.int32)
+    ref = Mesh(v.copy(), f.copy())
+    gv, gf = R.merge_vertices(torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda())
+    assert np.array_equal(gv.cpu().numpy(), ref.vertices)
+    assert np.array_equal(gf.cpu().numpy().astype(np.int64), ref.faces)
