@@ -209,7 +209,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
     const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
     const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
     uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
-    uint32_t full_ok = 0;  // W_FULL(stage) already seen complete by the probe issued one trip earlier
+    // One trip of the issue loop covers up to two ring stages (K = 256, 16 MMAs, 1024 tensor-pipe cycles) so
+    // that the loop's own latency (polls, election, descriptor set-up; ~100 dependent instructions of one
+    // warp) stays hidden behind the MMAs already queued.  ok0 / ok1: the two stages of the coming trip were
+    // already seen complete by the non-blocking probes issued one trip earlier.
+    uint32_t ok0 = 0, ok1 = 0;
     for (int64_t it = 0; it < iters; it++) {
       for (int net = 0; net < 2; net++) {
         if (!((P.net_mask >> net) & 1)) continue;
@@ -225,42 +229,62 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             { const long long t = tick(); ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u); w1 += tick() - t; }
             acc_it++;
             const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
-            uint64_t ad = a_desc0;
-            uint32_t at = tmem_base + TM_A;
+            // the 8 MMAs of ring stage st = K range [128 sidx, 128 sidx + 128) of this chunk
+            auto issue_stage = [&](uint32_t st, int sidx) {
+              const uint64_t bd = b_desc0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+              if (debug & 2) return;
+              if (src == 0) {
+                const uint64_t ad = a_desc0 + (uint64_t)(sidx * 2 * (A_CHUNK_BYTES >> 4));
+#pragma unroll
+                for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                  for (int k = 0; k < KCH / 16; k++)
+                    ptx::mma2_f16_ss(d_tmem, ad + (uint64_t)(kc * (A_CHUNK_BYTES >> 4) + 2 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
+                                     (uint32_t)((sidx | kc | k) != 0));
+              } else {
+                const uint32_t at = tmem_base + TM_A + (uint32_t)(sidx * KCH);
+#pragma unroll
+                for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                  for (int k = 0; k < KCH / 16; k++)
+                    ptx::mma2_f16_ts(d_tmem, at + (uint32_t)(kc * (KCH / 2) + 8 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
+                                     (uint32_t)((sidx | kc | k) != 0));
+              }
+            };
+            int sidx = 0;
 #pragma unroll 1
-            for (int s = 0; s < k_stages; s++) {
-              if (j == 0) { const long long t = tick(); ptx::mbar_spin_cluster(A_READY(src, s), (a_ph >> (4 * src + s)) & 1u); w2 += tick() - t; }
-              if (!full_ok) { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(stage), phase); w3 += tick() - t; }
+            while (sidx < k_stages) {
+              const bool two = sidx + 1 < k_stages;
+              const uint32_t st0 = stage, ph0 = phase;
+              const uint32_t st1 = (st0 + 1 == NSTAGES) ? 0u : st0 + 1, ph1 = ph0 ^ (uint32_t)(st1 == 0);
+              if (j == 0) {
+                const long long t = tick();
+                ptx::mbar_spin_cluster(A_READY(src, sidx), (a_ph >> (4 * src + sidx)) & 1u);
+                if (two) ptx::mbar_spin_cluster(A_READY(src, sidx + 1), (a_ph >> (4 * src + sidx + 1)) & 1u);
+                w2 += tick() - t;
+              }
+              if (!ok0) { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(st0), ph0); w3 += tick() - t; }
+              if (two && !ok1) { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(st1), ph1); w3 += tick() - t; }
               ptx::tc_fence_after();
-              // probe the next stage's barrier now: the poll's latency hides behind the MMA issue below
-              const uint32_t nstage = (stage + 1 == NSTAGES) ? 0u : stage + 1, nphase = phase ^ (uint32_t)(nstage == 0);
-              full_ok = ptx::mbar_test(W_FULL(nstage), nphase);
-              const uint64_t bd = b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4));
+              // probe the coming trip's barriers now: the polls' latency hides behind the MMA issue below
+              const uint32_t nst0 = two ? ((st1 + 1 == NSTAGES) ? 0u : st1 + 1) : st1;
+              const uint32_t nph0 = two ? (ph1 ^ (uint32_t)(nst0 == 0)) : ph1;
+              const uint32_t nst1 = (nst0 + 1 == NSTAGES) ? 0u : nst0 + 1, nph1 = nph0 ^ (uint32_t)(nst1 == 0);
+              ok0 = ptx::mbar_test(W_FULL(nst0), nph0);
+              ok1 = ptx::mbar_test(W_FULL(nst1), nph1);
               if (ptx::elect_one()) {
-                if (debug & 2) {
-                } else if (src == 0) {
-#pragma unroll
-                  for (int kc = 0; kc < 2; kc++)
-#pragma unroll
-                    for (int k = 0; k < KCH / 16; k++)
-                      ptx::mma2_f16_ss(d_tmem, ad + (uint64_t)(kc * (A_CHUNK_BYTES >> 4) + 2 * k), bd + (uint64_t)(kc * tile16 + 2 * k),
-                                       idesc, (uint32_t)((s | kc | k) != 0));
-                } else {
-#pragma unroll
-                  for (int kc = 0; kc < 2; kc++)
-#pragma unroll
-                    for (int k = 0; k < KCH / 16; k++)
-                      ptx::mma2_f16_ts(d_tmem, at + (uint32_t)(kc * (KCH / 2) + 8 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
-                                       (uint32_t)((s | kc | k) != 0));
+                issue_stage(st0, sidx);
+                ptx::mma2_commit(W_EMPTY(st0), 3);
+                if (two) {
+                  issue_stage(st1, sidx + 1);
+                  ptx::mma2_commit(W_EMPTY(st1), 3);
                 }
-                ptx::mma2_commit(W_EMPTY(stage), 3);
-                if (s == k_stages - 1) ptx::mma2_commit(ACC_FULL(buf), 3);
+                if (sidx + (two ? 2 : 1) == k_stages) ptx::mma2_commit(ACC_FULL(buf), 3);
               }
               __syncwarp();
-              ad += 2 * (A_CHUNK_BYTES >> 4);
-              at += KCH;
-              stage = nstage;
-              phase = nphase;
+              stage = nst0;
+              phase = nph0;
+              sidx += two ? 2 : 1;
             }
             if (j == 0) a_ph ^= ((1u << k_stages) - 1u) << (4 * src);
           }
