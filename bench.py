@@ -141,6 +141,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--query-only", action="store_true", help="diagnostics: time the grid query alone (not a bench line)")
+    ap.add_argument("--slab-dims", type=int, default=0,
+                    help="also time BASELINE configs[3]: ONE grid of this size sharded by axis-0 slabs over the ranks, "
+                         "fragments gathered to rank 0 over NCCL (adds a 'slab' object to the JSON line)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -229,6 +232,33 @@ def main():
     e2e_ms = 1e3 * (time.perf_counter() - w0)
     clocks = sampler.stop() if sampler else None
 
+    slab = None
+    if args.slab_dims:
+        from deepjoin_b200 import parallel as Par
+        sd = (args.slab_dims,) * 3
+        dec0 = util.make_decoder(0, "trained_norm", device=dev, precision=args.precision)  # same weights on every rank
+        code0 = util.trained_code(0).to(dev)
+        for _ in range(2):
+            m = Par.create_mesh_sharded(code0, dec0, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=sd, padding=0.1)
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        s0.record()
+        reps = 3
+        for _ in range(reps):
+            m = Par.create_mesh_sharded(code0, dec0, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=sd, padding=0.1)
+            barrier()
+        s1.record()
+        torch.cuda.synchronize()
+        ts = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            slab = {"workload": "configs[3]: %d^3 grid sharded by axis-0 slabs over %d GPU(s), NCCL gather of mesh fragments, "
+                                "mesh finished on rank 0 (host Mesh out)" % (args.slab_dims, world),
+                    "ms_per_mesh": float(ts[0]), "wall_ms_per_mesh": 1e3 * (time.perf_counter() - w0) / reps,
+                    "queries_per_s": args.slab_dims ** 3 / (float(ts[0]) * 1e-3),
+                    "vertices": int(len(m.vertices)), "faces": int(len(m.faces))}
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -252,11 +282,13 @@ def main():
                     "ms_per_step": e2e_ms / args.steps, "api": "deepjoin_b200.core.reconstruct.create_mesh"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "tc_forward_kernel" if args.precision == "bf16" else "sgemm_kernel",
+                         "traffic": None, "kernel": "tc2_forward_kernel" if args.precision == "bf16" else "sgemm_kernel",
                          "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step); burst %.1f" % (which, burst),
                          "flop_per_query": FLOP_ALG[u]},
             "clocks": clocks,
         }
+        if slab:
+            line["slab"] = slab
         if not args.no_cpu_baseline and world == 1:
             rate, done, dt, thr = cpu_decoder_rate(1 << 19, u)
             line["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": thr, "kind": "port",

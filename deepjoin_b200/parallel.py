@@ -48,3 +48,153 @@ def merge_slab_meshes(fragments, top_planes):
         prev_top, prev_offset = top_planes[k], offset
         offset += len(v)
     return np.concatenate(verts, 0), np.concatenate(faces, 0).astype(np.int32)
+
+
+# ---------------------------------------------------------------------------------------------
+# torch.distributed plumbing: the one exchange of the sharded path -- a gather of
+# mesh fragments to one rank (NCCL over NVLink on GPUs, gloo in the CPU tests).
+# ---------------------------------------------------------------------------------------------
+def _dist():
+    import torch.distributed as dist
+    return dist if (dist.is_available() and dist.is_initialized()) else None
+
+
+def gather_fragments(verts, faces, top, group=None, dst=0):
+    """Collective.  verts [V,3] float32, faces [F,3] int32 (slab-local ids, seam references
+    -2-slot), top [T] int32 (ids of the slab's last-plane edges) -- torch tensors on this rank's
+    device.  Returns the list of (verts, faces, top) over ranks on rank `dst`, None elsewhere.
+    Two collectives: an all-gather of the three counts, then ONE gather of a padded int32 buffer
+    (payload is a few MB: latency-bound, so a single call beats three)."""
+    import torch
+    dist = _dist()
+    verts = verts.reshape(-1, 3).to(torch.float32).contiguous()
+    faces = faces.reshape(-1, 3).to(torch.int32).contiguous()
+    top = top.reshape(-1).to(torch.int32).contiguous()
+    if dist is None or dist.get_world_size(group) == 1:
+        return [(verts, faces, top)]
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = verts.device
+    counts = torch.tensor([verts.shape[0], faces.shape[0], top.shape[0]], dtype=torch.int64, device=dev)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    all_counts = torch.stack(all_counts).cpu().tolist()
+    sizes = [3 * v + 3 * f + t for v, f, t in all_counts]
+    buf = torch.zeros(max(max(sizes), 1), dtype=torch.int32, device=dev)
+    nv3, nf3 = 3 * verts.shape[0], 3 * faces.shape[0]
+    buf[:nv3] = verts.reshape(-1).view(torch.int32)
+    buf[nv3:nv3 + nf3] = faces.reshape(-1)
+    buf[nv3 + nf3:nv3 + nf3 + top.shape[0]] = top
+    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
+    dist.gather(buf, bufs, dst=dst, group=group)
+    if rank != dst:
+        return None
+    out = []
+    for (v, f, t), b in zip(all_counts, bufs):
+        out.append((b[:3 * v].view(torch.float32).reshape(v, 3), b[3 * v:3 * v + 3 * f].reshape(f, 3),
+                    b[3 * v + 3 * f:3 * v + 3 * f + t]))
+    return out
+
+
+def merge_fragments(frags):
+    """merge_slab_meshes on torch tensors (any device): fragments in slab order -> (verts [V,3] f32,
+    faces [F,3] int32) with exactly the ids of the single sweep."""
+    import torch
+    verts, faces = [], []
+    offset, prev_top, prev_offset = 0, None, 0
+    for k, (v, f, top) in enumerate(frags):
+        f = f.to(torch.int64)
+        if k > 0:
+            seam = f < -1
+            ids = prev_top.to(torch.int64)[(-2 - f[seam])]
+            if bool((ids < 0).any()):
+                raise RuntimeError("slab %d references a seam edge the slab below never created" % k)
+            f = torch.where(seam, f, f + offset)
+            f[seam] = ids + prev_offset
+        verts.append(v)
+        faces.append(f)
+        prev_top, prev_offset = top, offset
+        offset += v.shape[0]
+    return torch.cat(verts, 0), torch.cat(faces, 0).to(torch.int32)
+
+
+def slab_fragment(vec, decoder, use_net, sigmoid, level, dims, padding, z_lo, z_hi, seam):
+    """One rank's share of create_mesh: query sample planes [z_lo, z_hi] of axis 0 (the flat rows
+    [z_lo*d1*d2, (z_hi+1)*d1*d2) of decode_shape) and run marching cubes on that slab.
+    Returns (verts f32 [V,3] in GLOBAL index units, faces int32 [F,3] slab-local ids with seam
+    references, top-plane id table int32 [d1*d2*3], (vmin, vmax) of the slab) -- CUDA tensors."""
+    import ctypes
+    import torch
+    from deepjoin_b200 import _lib
+    from deepjoin_b200.core import reconstruct as R
+    d0, d1, d2 = [int(d) for d in dims]
+    plane = d1 * d2
+    vol = R.decode_shape_device(vec, decoder, dims, use_net=use_net, padding=padding, sigmoid=sigmoid,
+                                rows=(z_lo * plane, (z_hi + 1) * plane))
+    dev = vol.device
+    mm = torch.aminmax(vol)
+    n0 = z_hi - z_lo + 1
+    if n0 < 2:  # a rank without cell layers contributes nothing
+        return (torch.empty((0, 3), dtype=torch.float32, device=dev), torch.empty((0, 3), dtype=torch.int32, device=dev),
+                torch.full((plane * 3,), -1, dtype=torch.int32, device=dev), mm)
+    w = R._work_for(dev.index)
+    nv, nf = ctypes.c_int64(), ctypes.c_int64()
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        st = _lib.stream_ptr()
+        _lib.check(L.dj_mc_count(w.handle, vol.data_ptr(), n0, d1, d2, int(z_lo), int(bool(seam)), float(level), 0,
+                                 ctypes.byref(nv), ctypes.byref(nf), st))
+        verts = torch.empty((nv.value, 3), device=dev, dtype=torch.float32)
+        faces = torch.empty((nf.value, 3), device=dev, dtype=torch.int32)
+        top = torch.empty(plane * 3, device=dev, dtype=torch.int32)
+        _lib.check(L.dj_mc_fill(w.handle, 0, verts.data_ptr(), faces.data_ptr(), st))
+        _lib.check(L.dj_mc_top_plane(w.handle, top.data_ptr(), st))
+    return verts, faces, top, mm
+
+
+def finish_mesh(verts, faces, dims, padding, gradient_direction):
+    """create_mesh after marching cubes (core/reconstruct.py:172-191) on device tensors: 'descent'
+    reverses the faces, spacing (1+2p)/d in float64, swap vertex columns 0/1, centre, trimesh's
+    duplicate-vertex merge.  Returns deepjoin_b200.mesh.Mesh."""
+    import torch
+    from deepjoin_b200.core import reconstruct as R
+    from deepjoin_b200.mesh import Mesh
+    if gradient_direction == "descent":
+        faces = torch.flip(faces, dims=[1])
+    sp = [(1 + (padding * 2)) / d for d in dims]
+    v = verts.to(torch.float64)
+    v = torch.stack([v[:, 1] * sp[1], v[:, 0] * sp[0], v[:, 2] * sp[2]], dim=1) - (0.5 + padding)
+    if v.is_cuda:
+        v, faces = R.merge_vertices(v, faces)
+        return Mesh(v.cpu().numpy(), faces.cpu().numpy(), process=False)
+    return Mesh(v.numpy(), faces.numpy())
+
+
+def create_mesh_sharded(vec, decoder, use_net, sigmoid=True, level=0.5, gradient_direction="descent", dims=(256, 256, 256),
+                        padding=0.1, group=None, dst=0):
+    """create_mesh (core/reconstruct.py:135-192) with the grid split into axis-0 slabs over the ranks of
+    `group` (BASELINE config 4).  Collective; every rank passes the same arguments and its own
+    decoder replica.  Returns the Mesh on rank `dst`, None elsewhere; raises
+    IsosurfaceExtractionError on EVERY rank under the reference's conditions."""
+    import torch
+    from deepjoin_b200.core import errors
+    dist = _dist()
+    world = dist.get_world_size(group) if dist else 1
+    rank = dist.get_rank(group) if dist else 0
+    if gradient_direction not in ("descent", "ascent"):
+        raise errors.IsosurfaceExtractionError
+    z_lo, z_hi = slab_ranges(int(dims[0]), world)[rank]
+    verts, faces, top, (vmin, vmax) = slab_fragment(vec, decoder, use_net, sigmoid, level, dims, padding, z_lo, z_hi,
+                                                    seam=rank > 0 and z_lo > 0)
+    stats = torch.stack([-vmin, vmax, torch.tensor(float(verts.shape[0]), device=vmin.device)]).to(torch.float64)
+    if dist and world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX, group=group)
+    lo, hi, most = (-stats[0]).item(), stats[1].item(), stats[2].item()
+    if level < lo or level > hi:
+        raise errors.IsosurfaceExtractionError("Surface level must be within volume data range.")
+    if most == 0:
+        raise errors.IsosurfaceExtractionError("No surface found at the given iso value.")
+    frags = gather_fragments(verts, faces, top, group=group, dst=dst)
+    if frags is None:
+        return None
+    v, f = merge_fragments(frags)
+    return finish_mesh(v, f, dims, padding, gradient_direction)

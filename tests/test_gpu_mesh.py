@@ -88,3 +88,35 @@ def test_device_vertex_merge_equals_host_merge(nv, dup_frac):
     gv, gf = R.merge_vertices(torch.from_numpy(v).cuda(), torch.from_numpy(f).cuda())
     assert np.array_equal(gv.cpu().numpy(), ref.vertices)
     assert np.array_equal(gf.cpu().numpy().astype(np.int64), ref.faces)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("direction", ["ascent", "descent"])
+def test_slab_sharded_create_mesh_is_byte_identical(world, direction):
+    """BASELINE config 4 on one GPU: the ranks' slab fragments computed one after the other, merged as the
+    gather step does, finished as create_mesh does -> identical to the unsharded create_mesh."""
+    from deepjoin_b200 import parallel as P
+    from deepjoin_b200.core import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision="bf16")
+    code = util.trained_code(0)
+    dims = (48, 40, 44)
+    ref = R.create_mesh(code, dec, 1, sigmoid=False, level=0.0, gradient_direction=direction, dims=dims, padding=0.1)
+    frags = []
+    for k, (lo, hi) in enumerate(P.slab_ranges(dims[0], world)):
+        v, f, top, _ = P.slab_fragment(code, dec, 1, False, 0.0, dims, 0.1, lo, hi, seam=k > 0 and lo > 0)
+        frags.append((v.clone(), f.clone(), top.clone()))
+    v, f = P.merge_fragments(frags)
+    mesh = P.finish_mesh(v, f, dims, 0.1, direction)
+    assert np.array_equal(mesh.faces, ref.faces) and np.array_equal(mesh.vertices, ref.vertices)
+    # world size 1 (no process group): the collective entry point degenerates to create_mesh
+    one = P.create_mesh_sharded(code, dec, 1, sigmoid=False, level=0.0, gradient_direction=direction, dims=dims, padding=0.1)
+    assert np.array_equal(one.faces, ref.faces) and np.array_equal(one.vertices, ref.vertices)
+
+
+def test_slab_sharded_create_mesh_raises_like_the_reference():
+    from deepjoin_b200 import parallel as P
+    from deepjoin_b200.core import errors
+    dec = util.make_decoder(0, "default", precision="fp32")  # degenerate field: no zero crossing
+    code = util.code_for(0, "default")
+    with pytest.raises(errors.IsosurfaceExtractionError):
+        P.create_mesh_sharded(code, dec, 0, sigmoid=False, level=0.0, gradient_direction="ascent", dims=(16, 16, 16))
