@@ -4,6 +4,7 @@
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
 #include "mlp_tc2.cuh"
+#include "latent_tc2.cuh"
 #include "mc.cuh"
 #include "sampler.cuh"
 #include "mesh_merge.cuh"
@@ -30,13 +31,18 @@ struct DjPack {
   uint8_t* stream2[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   tc2::Net nets2[2];
   unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
+  // fused forward+backward program of the latent step (latent_tc2.cuh)
+  uint8_t* lat_stream[2] = {nullptr, nullptr};
+  lat2::Layer lat_prog[lat2::MAX_PROG];
+  int lat_n_prog = 0;
+  bool lat_attr_set = false;
   int tc_kernel = 2;  // 2: CTA-pair kernel (default); 1: single-CTA kernel (env DEEPJOIN_B200_TC=1)
   // per-call shape constants + device error word
   float4* tables = nullptr;
   unsigned int* err = nullptr;
   simt::FoldParams fold{};
   // workspaces (grow only)
-  DevBuf ws_fwd, ws_lat, ws_host, ws_vol;
+  DevBuf ws_fwd, ws_lat, ws_host, ws_vol, ws_mask;
   bool tc_attr_set = false, tc_attr_set2 = false;
   int tc_cluster = 2;  // CTAs sharing one weight stream (1, 2 or 4); env DEEPJOIN_B200_CLUSTER
 };
@@ -54,6 +60,8 @@ static void free_pack(DjPack* p) {
       if (p->stream2[i][r]) cudaFree(p->stream2[i][r]);
   }
   if (p->bias_dev) cudaFree(p->bias_dev);
+  for (int r = 0; r < 2; r++)
+    if (p->lat_stream[r]) cudaFree(p->lat_stream[r]);
   if (p->tables) cudaFree(p->tables);
   if (p->err) cudaFree(p->err);
   if (p->prof) cudaFree(p->prof);
@@ -61,6 +69,7 @@ static void free_pack(DjPack* p) {
   p->ws_lat.release();
   p->ws_host.release();
   p->ws_vol.release();
+  p->ws_mask.release();
   delete p;
 }
 
@@ -71,6 +80,35 @@ static void pack_tile(const float* W, int ldw, int n_real, int k_real, int n0, i
     for (int k = 0; k < 64; k++) {
       const int gn = n0 + r, gk = k0 + k;
       const float v = (gn < n_real && gk < k_real) ? W[(size_t)gn * ldw + gk] : 0.f;
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      memcpy(dst + off, &b, 2);
+    }
+}
+
+
+// transposed source: tile row n, column k <- W[k0 + k][n0 + n]  (B operand of a backward GEMM, dX = dY . W)
+static void pack_tile_T(const float* W, int ldw, int out_real, int in_real, int n0, int k0, int rows, uint8_t* dst) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      const int gn = n0 + r, gk = k0 + k;  // gn: input index of the layer (output column of the backward GEMM), gk: its output index
+      const float v = (gn < in_real && gk < out_real) ? W[(size_t)gk * ldw + gn] : 0.f;
+      const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      memcpy(dst + off, &b, 2);
+    }
+}
+// head-gradient tile: row n (hidden unit), K = 16 slots [W_head[0..4][n] | W_head[0..4][n] | lo(W_head[0..4][n]) | 0]
+// against the operand [g_hi | g_lo | g_hi | 0] (latent_tc2.cuh:write_head_operand)
+static void pack_tile_head_T(const float* Wh, int ldw, int n0, int rows, uint8_t* dst) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      float v = 0.f;
+      if (k < 15) {
+        const float w = Wh[(size_t)(k % 5) * ldw + n0 + r];
+        const float hi = __bfloat162float(__float2bfloat16_rn(w));
+        v = (k < 10) ? hi : (w - hi);
+      }
       const __nv_bfloat16 b = __float2bfloat16_rn(v);
       const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
       memcpy(dst + off, &b, 2);
@@ -256,6 +294,93 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       DJ_TRY(cudaMalloc((void**)&p->stream2[net][r], blob[r].size()));
       DJ_TRY(cudaMemcpy(p->stream2[net][r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
       N.stream[r] = p->stream2[net][r];
+    }
+  }
+  // ---- latent-step program (latent_tc2.cuh): forward, loss, backward in one pass over the tile
+  {
+    const int nlf = d->f_layers, nlh = d->h_layers;
+    if ((nlf - 1) + (nlh - 1) + 2 > lat2::MASK_LAYERS + 2 || nlf - 1 + nlh - 1 != lat2::MASK_LAYERS)
+      return bail(fail(DJ_ERR_UNSUPPORTED, "latent step: %d + %d hidden activations (built for %d)", nlf - 1, nlh - 1, lat2::MASK_LAYERS));
+    std::vector<uint8_t> blob[2];
+    int np = 0;
+    auto add = [&](int kind, int src, int dst, int n_chunks, int k_stages, int k_steps, int mma_n, int mask_layer, int slot,
+                   int bias_off, int after) -> lat2::Layer& {
+      lat2::Layer& T = p->lat_prog[np++];
+      memset(&T, 0, sizeof T);
+      T.kind = (int8_t)kind; T.src = (int8_t)src; T.dst = (int8_t)dst; T.k_steps = (int8_t)k_steps;
+      T.n_chunks = (int8_t)n_chunks; T.k_stages = (int8_t)k_stages; T.mask_layer = (int8_t)mask_layer; T.slot = (int8_t)slot;
+      T.mma_n = (int16_t)mma_n; T.after = (int16_t)after; T.bias_off = bias_off;
+      T.tile_bytes = (mma_n / 2) * 128;
+      T.stage_bytes = (k_steps == 1 ? 1 : 2) * T.tile_bytes;
+      return T;
+    };
+    // stages of one layer: chunk-major, then K; each CTA rank gets rows [r*mma_n/2, ...) of every chunk
+    auto emit = [&](const lat2::Layer& T, auto&& tile_fn) {
+      const int rows = T.mma_n / 2;
+      for (int j = 0; j < T.n_chunks; j++)
+        for (int st = 0; st < T.k_stages; st++)
+          for (int r = 0; r < 2; r++)
+            for (int kc = 0; kc < (T.k_steps == 1 ? 1 : 2); kc++) {
+              const size_t o = blob[r].size();
+              blob[r].resize(o + T.tile_bytes);
+              tile_fn(j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blob[r].data() + o);
+            }
+    };
+    int buf = 0;  // where the current activations live: 0 shared memory, 1 tensor memory
+    int mask = 0;
+    for (int net = 0; net < 2; net++) {
+      const int nl = net == 0 ? nlf : nlh;
+      const float* const* W = net == 0 ? f_w : h_w;
+      const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
+      const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
+      const tc2::Net& N2 = p->nets2[net];
+      add(lat2::K_L0, 2, 0, 0, 0, 0, 0, mask++, net == 0 ? 0 : 2, 0, 0);
+      buf = 0;
+      for (int l = 1; l < nl; l++) {
+        const tc2::Layer& F = N2.layers[l - 1];
+        const bool head = (l == nl - 1);
+        const bool reinj = (net == 0 && l == li);
+        const int k_real = reinj ? K3 : ins[l];
+        const int kind = head ? (net == 0 ? lat2::K_HEAD_F : lat2::K_HEAD_H) : (reinj ? lat2::K_FWD_XYZ : lat2::K_FWD);
+        lat2::Layer& T = add(kind, buf, head ? 2 : 1 - buf, F.n_chunks, F.k_stages, 8, F.mma_n, head ? 0 : mask, reinj ? 1 : 0,
+                             F.bias_off, 0);
+        emit(T, [&](int n0, int k0, int rows, uint8_t* dst) { pack_tile(W[l], ins[l], outs[l], k_real, n0, k0, rows, dst); });
+        if (!head) { mask++; buf = 1 - buf; }
+      }
+    }
+    // backward: hnet first (its head operand is written right after the loss), then fnet
+    for (int net = 1; net >= 0; net--) {
+      const int nl = net == 0 ? nlf : nlh;
+      const float* const* W = net == 0 ? f_w : h_w;
+      const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
+      const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
+      const int mask0 = net == 0 ? 0 : nlf - 1;  // mask layer of this net's layer-0 output
+      // head: K = 16 operand in shared memory -> gradient of the last hidden activation, into tensor memory
+      {
+        lat2::Layer& T = add(lat2::K_BWD, 0, 1, 4, 1, 1, 128, mask0 + nl - 2, 0, 0, 0);
+        emit(T, [&](int n0, int, int rows, uint8_t* dst) { pack_tile_head_T(W[nl - 1], ins[nl - 1], n0, rows, dst); });
+      }
+      buf = 1;
+      for (int l = nl - 2; l >= 1; l--) {
+        // gradient wrt the input of layer l (= output of layer l-1, mask layer mask0 + l - 1)
+        const bool reinj = (net == 0 && l == li);
+        const int in_real = reinj ? K3 : ins[l];              // columns of W_l that multiply hidden activations
+        const int out_real = outs[l];                          // contraction length
+        const int n_chunks = (in_real + 127) / 128, k_stages = ((out_real + 127) / 128);
+        const bool last = (l == 1);
+        const bool summed = last || (net == 0 && l - 1 == li);  // dPre of layer 0 / of the re-injection layer
+        const int kind = last ? lat2::K_SUM : (summed ? lat2::K_BWD_SUM : lat2::K_BWD);
+        const int slot = last ? (net == 0 ? 0 : 2) : 1;
+        lat2::Layer& T = add(kind, buf, last ? 2 : 1 - buf, n_chunks, k_stages, 8, 128, mask0 + l - 1, slot, 0,
+                             (last && net == 1) ? 1 : 0);
+        emit(T, [&](int n0, int k0, int rows, uint8_t* dst) { pack_tile_T(W[l], ins[l], out_real, in_real, n0, k0, rows, dst); });
+        buf = 1 - buf;
+      }
+    }
+    p->lat_n_prog = np;
+    for (int r = 0; r < 2; r++) {
+      DJ_TRY(cudaMalloc((void**)&p->lat_stream[r], blob[r].size()));
+      DJ_TRY(cudaMemcpy(p->lat_stream[r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
     }
   }
   DJ_TRY(upload(bias_host.data(), bias_host.size(), &p->bias_dev));
@@ -527,9 +652,10 @@ struct LatWs {
   float *yC, *yT, *dyC, *dyT, *G0, *G1, *colsum, *loss_acc, *grad, *terms, *bx, *bs, *bn;
 };
 
-static int carve_latent(DjPack* p, int64_t n, LatWs& W) {
+// small: the tensor-core path keeps no activations in global memory
+static int carve_latent(DjPack* p, int64_t n, LatWs& W, bool small = false) {
   const int nf = p->desc.f_layers - 1, nh = p->desc.h_layers - 1;
-  const size_t act = (size_t)n * 512;
+  const size_t act = small ? 0 : (size_t)n * 512;
   const size_t floats = (size_t)(nf + nh + 2) * act + 4 * (size_t)n * 8 + 3 * 512 + 8 + 256 + 8 + (size_t)n * 7 + 64;
   DJ_CUDA(p->ws_lat.reserve(floats * sizeof(float)));
   float* q = p->ws_lat.as<float>();
@@ -604,10 +730,52 @@ static int latent_fwd_bwd(DjPack* p, const float* code_dev, const float* xyz, co
   return DJ_OK;
 }
 
+// tensor-core forward + loss + backward (latent_tc2.cuh); same outputs as latent_fwd_bwd.  idx (optional):
+// the mini-batch's rows of the pool, gathered inside the kernel.
+static int latent_fwd_bwd_tc(DjPack* p, const float* code_dev, const float* xyz, const float* sdf, const float* nrm,
+                             const int32_t* idx, int64_t n, const DjLatentCfg* cfg, LatWs& W, cudaStream_t st) {
+  int rc;
+  if ((rc = launch_fold(p, code_dev, st))) return rc;
+  DJ_CUDA(cudaMemsetAsync(W.colsum, 0, (3 * 512 + 8) * sizeof(float), st));  // colsum + loss_acc are contiguous
+  const int64_t ntiles = (n + lat2::TILE_M - 1) / lat2::TILE_M;
+  const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);
+  const int64_t passes = (ntiles + grid - 1) / grid;
+  DJ_CUDA(p->ws_mask.reserve((size_t)passes * grid * lat2::MASK_LAYERS * 8 * 128 * sizeof(unsigned long long)));
+  lat2::Params P;
+  memset(&P, 0, sizeof P);
+  memcpy(P.prog, p->lat_prog, sizeof(lat2::Layer) * p->lat_n_prog);
+  P.n_prog = p->lat_n_prog;
+  P.stream[0] = p->lat_stream[0];
+  P.stream[1] = p->lat_stream[1];
+  P.bias = p->bias_dev;
+  P.tables = p->tables;
+  P.xyz = xyz; P.sdf = sdf; P.nrm = nrm; P.idx = idx;
+  P.n = n;
+  P.loss = simt::LossCfg{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, p->desc.slope, 1.0f / (float)n};
+  P.masks = p->ws_mask.as<unsigned long long>();
+  P.colsum = W.colsum;
+  P.loss_acc = W.loss_acc;
+  P.err = p->err;
+  if (!p->lat_attr_set) {
+    DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
+    p->lat_attr_set = true;
+  }
+  lat2::latent_tc2_kernel<<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
+  DJ_LAUNCHED();
+  simt::GradFinishParams GP;
+  for (int i = 0; i < 3; i++) { GP.src[i] = p->fold.src[i]; GP.colsum[i] = W.colsum + i * 512; }
+  GP.L = p->L; GP.Lb = p->Lb;
+  GP.reg_lambda = cfg->l2reg ? cfg->code_reg_lambda : 0.f;
+  simt::grad_finish_kernel<<<p->L + p->Lb, 128, 0, st>>>(GP, code_dev, W.grad, W.loss_acc);
+  DJ_LAUNCHED();
+  simt::loss_finish_kernel<<<1, 32, 0, st>>>(W.loss_acc, W.terms);
+  DJ_LAUNCHED();
+  return DJ_OK;
+}
+
 static int check_latent_cfg(DjPack* p, const DjLatentCfg* cfg) {
   if (!cfg) return fail(DJ_ERR_INVALID, "null DjLatentCfg");
-  if (cfg->precision != DJ_PREC_FP32)
-    return fail(DJ_ERR_UNSUPPORTED, "latent gradient: only DJ_PREC_FP32 is implemented (tensor-core backward is not built yet)");
+  if (cfg->precision != DJ_PREC_FP32 && cfg->precision != DJ_PREC_BF16) return fail(DJ_ERR_INVALID, "latent gradient: unknown precision %d", cfg->precision);
   if (p->L + p->Lb > 256) return fail(DJ_ERR_UNSUPPORTED, "code length > 256");
   return DJ_OK;
 }
@@ -621,8 +789,11 @@ extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz
   DeviceGuard g(p->device);
   cudaStream_t st = (cudaStream_t)stream;
   LatWs W;
-  if ((rc = carve_latent(p, n, W))) return rc;
-  if ((rc = latent_fwd_bwd(p, code_dev, xyz_dev, sdf_dev, nrm_dev, n, cfg, W, st))) return rc;
+  if ((rc = carve_latent(p, n, W, cfg->precision == DJ_PREC_BF16))) return rc;
+  if (cfg->precision == DJ_PREC_BF16) rc = latent_fwd_bwd_tc(p, code_dev, xyz_dev, sdf_dev, nrm_dev, nullptr, n, cfg, W, st);
+  else rc = latent_fwd_bwd(p, code_dev, xyz_dev, sdf_dev, nrm_dev, n, cfg, W, st);
+  if (rc) return rc;
+  if (cfg->precision == DJ_PREC_BF16 && (rc = check_err_word(p, st))) return rc;
   DJ_CUDA(cudaMemcpyAsync(grad_dev, W.grad, (p->L + p->Lb) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (loss_terms_dev) DJ_CUDA(cudaMemcpyAsync(loss_terms_dev, W.terms, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return DJ_OK;
@@ -641,13 +812,18 @@ extern "C" int dj_latent_optimize(DjPack* p, float* code_dev, float* adam_m_dev,
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t n = cfg->num_samples;
   LatWs W;
-  if ((rc = carve_latent(p, n, W))) return rc;
+  if ((rc = carve_latent(p, n, W, cfg->precision == DJ_PREC_BF16))) return rc;
   const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
   simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations};
   for (int e = 0; e < cfg->num_iterations; e++) {
-    simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, idx_dev + (size_t)e * n, (int)n, W.bx, W.bs, W.bn);
-    DJ_LAUNCHED();
-    if ((rc = latent_fwd_bwd(p, code_dev, W.bx, W.bs, W.bn, n, cfg, W, st))) return rc;
+    if (cfg->precision == DJ_PREC_BF16) {
+      // the kernel gathers the mini-batch rows itself
+      if ((rc = latent_fwd_bwd_tc(p, code_dev, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, idx_dev + (size_t)e * n, n, cfg, W, st))) return rc;
+    } else {
+      simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, idx_dev + (size_t)e * n, (int)n, W.bx, W.bs, W.bn);
+      DJ_LAUNCHED();
+      if ((rc = latent_fwd_bwd(p, code_dev, W.bx, W.bs, W.bn, n, cfg, W, st))) return rc;
+    }
     float* row = (log_dev && e % log_every == 0) ? log_dev + (size_t)(e / log_every) * 8 : nullptr;
     simt::adam_kernel<<<1, 256, 0, st>>>(A, e, code_dev, adam_m_dev, adam_v_dev, W.grad, p->L + p->Lb, W.terms, row, p->L);
     DJ_LAUNCHED();

@@ -1,0 +1,520 @@
+// Fused forward + backward of the joint decoder for the latent-code optimisation, on tcgen05 tensor
+// cores (sm_100a, CTA pairs / cta_group::2).  One launch = one Adam iteration's worth of decoder work.
+//
+// replaces, per iteration of reconstruct() (reconstruct.py:107-224): the decoder forward on the
+// mini-batch (:147), the clamped-L1 + BCE + normal loss (:166-192) and loss.backward() (:223) --
+// restricted to what the optimiser needs: the reference back-propagates into all decoder weights and
+// throws that away; only d loss / d [latent, break_latent] is consumed (reconstruct.py:58).
+//
+// Per tile of 128 samples per CTA (256 per pair) the kernel walks a 28-entry layer program without the
+// activations ever leaving the SM (same machinery as mlp_tc2.cuh: weights streamed by the TMA engine
+// through an mbarrier ring, A operand ping-ponging between shared and tensor memory, two accumulator
+// buffers in TMEM, MMAs issued by the leader CTA for the pair):
+//   forward   fnet layer 0 (CUDA cores) -> lin1..lin7 -> head;  hnet layer 0 -> lin1..lin4 -> head.
+//             Every hidden drain also records the SIGN of its 64 outputs (LeakyReLU'(x) is all the
+//             backward needs of a hidden layer): one 64-bit word per thread and chunk, 832 B per sample
+//             for the 13 hidden layers, written to and read back from global memory by the SAME thread.
+//   loss      in registers of the thread that owns the sample: heads, B = select(C, T), clamped L1 / BCE /
+//             normal MSE, d loss / d head pre-activations (simt::loss_row, shared with the fp32 path);
+//             loss terms reduced by warp shuffles -> 3 atomics per warp.
+//   backward  d head (10 numbers per sample, split hi/lo into a K = 16 bf16 operand) x W_head^T, then
+//             dPre_l = (dPre_{l+1} . W_{l+1}) * LeakyReLU'(pre_l) through the transposed weight stream.
+//             The three activations the code enters through (fnet lin0, the re-injection layer, hnet
+//             lin0) are column-summed over the tile (warp transpose-reduce -> atomics into colsum[3][512]);
+//             grad_finish_kernel turns those into d loss / d code exactly as the fp32 path does.
+// Arithmetic: bf16 operands, fp32 accumulation, fp32 loss; the gradient carries bf16 rounding noise
+// (~1e-2 relative), the loss terms are those of the bf16 forward.  DJ_PREC_FP32 keeps the exact path.
+#pragma once
+#include <type_traits>
+#include "mlp_simt.cuh"
+#include "mlp_tc2.cuh"
+
+namespace dj {
+namespace lat2 {
+
+using tc2::A_CHUNK_BYTES;
+using tc2::EPI_WARPS;
+using tc2::KCH;
+using tc2::NCH;
+using tc2::NEPI;
+using tc2::NSTAGES;
+using tc2::NTHREADS;
+using tc2::SM_A;
+using tc2::SM_BAR;
+using tc2::SM_BIAS;
+using tc2::SM_TAB;
+using tc2::SM_W;
+using tc2::SMEM_BYTES;
+using tc2::STAGE_BYTES;
+using tc2::TILE_M;
+using tc2::TM_A;
+using tc2::TM_ACC;
+
+constexpr int MAX_PROG = 32;
+constexpr int MASK_LAYERS = 13;  // hidden activations whose sign the backward needs (8 fnet + 5 hnet)
+
+enum {
+  K_L0 = 0,        // epilogue only: layer 0 on CUDA cores -> shared-memory activations
+  K_FWD = 1,       // hidden layer: + bias, LeakyReLU, -> bf16, record signs
+  K_FWD_XYZ = 2,   // the re-injection layer: + (w_xyz . xyz + c) instead of a bias
+  K_HEAD_F = 3,    // fnet head: 5 pre-activations into registers
+  K_HEAD_H = 4,    // hnet head (+ its LeakyReLU), then the loss and the hnet head gradient operand
+  K_BWD = 5,       // acc * LeakyReLU'(sign) -> bf16
+  K_BWD_SUM = 6,   // same + column sums into colsum[slot]
+  K_SUM = 7,       // column sums only (nothing consumes this gradient as a GEMM operand)
+};
+
+struct Layer {
+  int8_t kind, src, dst, k_steps;   // src / dst: 0 shared memory, 1 tensor memory, 2 none; k_steps: MMAs per ring stage
+  int8_t n_chunks, k_stages, mask_layer, slot;  // slot: colsum slot (K_BWD_SUM / K_SUM), table id (K_L0 / K_FWD_XYZ)
+  int16_t mma_n, after;             // after: 1 = write the fnet head gradient operand after this layer's last chunk
+  int32_t bias_off;
+  int32_t stage_bytes, tile_bytes;
+};
+struct Params {
+  Layer prog[MAX_PROG];
+  int32_t n_prog, debug;
+  const uint8_t* stream[2];  // per cluster rank, stages in program order
+  const float* bias;
+  const float4* tables;      // [3][512] per-shape constants (fold_kernel)
+  const float* xyz;          // sample pool or batch [.,3]
+  const float* sdf;          // [.]
+  const float* nrm;          // [.,3]
+  const int32_t* idx;        // nullptr: rows 0..n-1; else the mini-batch's row indices into the pool
+  int64_t n;
+  simt::LossCfg loss;
+  unsigned long long* masks;  // [tiles][MASK_LAYERS][4][2][128]
+  float* colsum;              // [3][512], zeroed by the caller
+  float* loss_acc;            // [8],     zeroed by the caller
+  unsigned int* err;
+};
+
+// warp transpose-reduce: on return lane L holds sum over the 32 lanes of v[L] (in v[0]) -- 31 shuffles
+__device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; i++) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_tc2_kernel(const __grid_constant__ Params P) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t sA = base + SM_A, sW = base + SM_W;
+  float* sBias = reinterpret_cast<float*>(smem + SM_BIAS);
+  float4* sTab = reinterpret_cast<float4*>(smem + SM_TAB);
+  const uint32_t bar0 = base + SM_BAR;
+  auto W_FULL = [&](int s) { return bar0 + 8u * s; };
+  auto W_EMPTY = [&](int s) { return bar0 + 8u * (NSTAGES + s); };
+  auto A_READY = [&](int b, int j) { return bar0 + 8u * (2 * NSTAGES + 4 * b + j); };
+  auto ACC_FULL = [&](int i) { return bar0 + 8u * (2 * NSTAGES + 8 + i); };
+  auto ACC_EMPTY = [&](int i) { return bar0 + 8u * (2 * NSTAGES + 10 + i); };
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 12));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+  const int64_t iters = (ntiles + gridDim.x - 1) / gridDim.x;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < NSTAGES; s++) {
+      ptx::mbar_init(W_FULL(s), rank == 0 ? 2 : 1);
+      ptx::mbar_init(W_EMPTY(s), 1);
+    }
+    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(0, c), 2 * EPI_WARPS);
+    for (int i = 0; i < 2; i++) {
+      ptx::mbar_init(ACC_FULL(i), 1);
+      ptx::mbar_init(ACC_EMPTY(i), 2 * EPI_WARPS);
+    }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(ptx::smem_u32((const void*)tmem_slot), 512);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer: this CTA's half of every stage, program order =====================
+    uint32_t stage = 0, phase = 0;
+    for (int64_t it = 0; it < iters; it++) {
+      const uint8_t* src = P.stream[rank];
+      for (int l = 0; l < P.n_prog; l++) {
+        const int ns = P.prog[l].n_chunks * P.prog[l].k_stages;
+        const uint32_t bytes = (uint32_t)P.prog[l].stage_bytes;
+        for (int s = 0; s < ns; s++) {
+          ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage);
+          if (ptx::elect_one()) {
+            ptx::mbar_expect_tx(W_FULL(stage), bytes);
+            ptx::bulk_g2s(sW + stage * STAGE_BYTES, src, bytes, W_FULL(stage));
+          }
+          __syncwarp();
+          src += bytes;
+          if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && rank != 0) {
+    // ===================== peer: relay "my half of the stage has landed" to the leader =====================
+    int per_pass = 0;
+    for (int l = 0; l < P.n_prog; l++) per_pass += P.prog[l].n_chunks * P.prog[l].k_stages;
+    const uint32_t lead_full0 = ptx::mapa(W_FULL(0), 0);
+    uint32_t stage = 0, phase = 0;
+    for (int64_t i = 0; i < iters * per_pass; i++) {
+      ptx::mbar_spin(W_FULL(stage), phase);
+      if (ptx::elect_one()) ptx::mbar_arrive_cluster(lead_full0 + 8u * stage);
+      __syncwarp();
+      if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp == 1) {
+    // ===================== leader: MMA issuer for the pair =====================
+    const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
+    const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
+    const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
+    uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
+    uint32_t ok0 = 0, ok1 = 0;
+    for (int64_t it = 0; it < iters; it++) {
+      for (int l = 0; l < P.n_prog; l++) {
+        const int n_chunks = P.prog[l].n_chunks, k_stages = P.prog[l].k_stages, k_steps = P.prog[l].k_steps;
+        if (n_chunks == 0) continue;  // epilogue-only entry
+        const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)P.prog[l].mma_n);
+        const uint32_t tile16 = (uint32_t)P.prog[l].tile_bytes >> 4;
+        const int src = P.prog[l].src;
+        for (int j = 0; j < n_chunks; j++) {
+          const uint32_t buf = acc_it & 1u;
+          ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u);
+          acc_it++;
+          const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
+          auto issue_stage = [&](uint32_t st, int sidx) {
+            const uint64_t bd = b_desc0 + (uint64_t)(st * (STAGE_BYTES >> 4));
+            if (k_steps == 1) {  // K = 16 operand (head gradient): one MMA, A in the first 32 B of the shared-memory rows
+              ptx::mma2_f16_ss(d_tmem, a_desc0, bd, idesc, 0u);
+              return;
+            }
+            if (src == 0) {
+              const uint64_t ad = a_desc0 + (uint64_t)(sidx * 2 * (A_CHUNK_BYTES >> 4));
+#pragma unroll
+              for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                for (int k = 0; k < KCH / 16; k++)
+                  ptx::mma2_f16_ss(d_tmem, ad + (uint64_t)(kc * (A_CHUNK_BYTES >> 4) + 2 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
+                                   (uint32_t)((sidx | kc | k) != 0));
+            } else {
+              const uint32_t at = tmem_base + TM_A + (uint32_t)(sidx * KCH);
+#pragma unroll
+              for (int kc = 0; kc < 2; kc++)
+#pragma unroll
+                for (int k = 0; k < KCH / 16; k++)
+                  ptx::mma2_f16_ts(d_tmem, at + (uint32_t)(kc * (KCH / 2) + 8 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
+                                   (uint32_t)((sidx | kc | k) != 0));
+            }
+          };
+          int sidx = 0;
+#pragma unroll 1
+          while (sidx < k_stages) {
+            const bool two = sidx + 1 < k_stages;
+            const uint32_t st0 = stage, ph0 = phase;
+            const uint32_t st1 = (st0 + 1 == NSTAGES) ? 0u : st0 + 1, ph1 = ph0 ^ (uint32_t)(st1 == 0);
+            if (j == 0) {
+              ptx::mbar_spin_cluster(A_READY(src, sidx), (a_ph >> (4 * src + sidx)) & 1u);
+              if (two) ptx::mbar_spin_cluster(A_READY(src, sidx + 1), (a_ph >> (4 * src + sidx + 1)) & 1u);
+            }
+            if (!ok0) ptx::mbar_spin_cluster(W_FULL(st0), ph0);
+            if (two && !ok1) ptx::mbar_spin_cluster(W_FULL(st1), ph1);
+            ptx::tc_fence_after();
+            const uint32_t nst0 = two ? ((st1 + 1 == NSTAGES) ? 0u : st1 + 1) : st1;
+            const uint32_t nph0 = two ? (ph1 ^ (uint32_t)(nst0 == 0)) : ph1;
+            const uint32_t nst1 = (nst0 + 1 == NSTAGES) ? 0u : nst0 + 1, nph1 = nph0 ^ (uint32_t)(nst1 == 0);
+            ok0 = ptx::mbar_test(W_FULL(nst0), nph0);
+            ok1 = ptx::mbar_test(W_FULL(nst1), nph1);
+            if (ptx::elect_one()) {
+              issue_stage(st0, sidx);
+              ptx::mma2_commit(W_EMPTY(st0), 3);
+              if (two) {
+                issue_stage(st1, sidx + 1);
+                ptx::mma2_commit(W_EMPTY(st1), 3);
+              }
+              if (sidx + (two ? 2 : 1) == k_stages) ptx::mma2_commit(ACC_FULL(buf), 3);
+            }
+            __syncwarp();
+            stage = nst0;
+            phase = nph0;
+            sidx += two ? 2 : 1;
+          }
+          if (j == 0) a_ph ^= ((1u << k_stages) - 1u) << (4 * src);
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps; thread = (sample row, 64-column half of a chunk) ==========
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_row = sA + row * 128;
+    const int sw = row & 7;
+    const float slope = P.loss.slope;
+    const uint64_t slope2 = ptx::pack_f32x2(slope, slope);
+    const uint32_t lead_aready0 = ptx::mapa(A_READY(0, 0), 0);
+    const uint32_t lead_accempty0 = ptx::mapa(ACC_EMPTY(0), 0);
+    uint32_t acc_it = 0;
+
+    // the K = 16 bf16 operand of a head-gradient GEMM in the first 32 B of this sample's shared-memory row:
+    // [g_hi(5) | g_lo(5) | g_hi(5) | 0], matching the rows [W, W, W_lo] of the packed head tile
+    auto write_head_operand = [&](const float (&gv)[5]) {
+      if (h == 0) {
+        uint32_t w[8];
+        float hi[5], lo[5];
+#pragma unroll
+        for (int i = 0; i < 5; i++) {
+          hi[i] = __bfloat162float(__float2bfloat16_rn(gv[i]));
+          lo[i] = gv[i] - hi[i];
+        }
+        const float k[16] = {hi[0], hi[1], hi[2], hi[3], hi[4], lo[0], lo[1], lo[2], lo[3], lo[4],
+                             hi[0], hi[1], hi[2], hi[3], hi[4], 0.f};
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = ptx::pack_bf16x2(k[2 * i], k[2 * i + 1]);
+        tc::st_shared_v4(a_row + ((0 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+        tc::st_shared_v4(a_row + ((1 ^ sw) << 4), w[4], w[5], w[6], w[7]);
+      }
+      ptx::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0);  // A_READY(shared, K range 0)
+    };
+
+    for (int64_t it = 0; it < iters; it++) {
+      const int64_t tile = it * gridDim.x + blockIdx.x;
+      const int64_t g = tile * TILE_M + row;
+      const bool live = g < P.n;
+      float x = 0.f, y = 0.f, z = 0.f, s_gt = 0.f, n_gt[3] = {0.f, 0.f, 0.f};
+      if (live) {
+        const int64_t r = P.idx ? (int64_t)__ldg(P.idx + g) : g;
+        x = __ldg(P.xyz + 3 * r); y = __ldg(P.xyz + 3 * r + 1); z = __ldg(P.xyz + 3 * r + 2);
+        if (h == 0) {
+          s_gt = __ldg(P.sdf + r);
+          n_gt[0] = __ldg(P.nrm + 3 * r); n_gt[1] = __ldg(P.nrm + 3 * r + 1); n_gt[2] = __ldg(P.nrm + 3 * r + 2);
+        }
+      }
+      unsigned long long* mrow = P.masks + ((size_t)tile * MASK_LAYERS * 8 + (size_t)h) * 128 + row;  // + (layer*4 + chunk)*256
+      float yc[5] = {0, 0, 0, 0, 0}, yt[5] = {0, 0, 0, 0, 0};
+      float gc[5] = {0, 0, 0, 0, 0};
+
+      for (int l = 0; l < P.n_prog; l++) {
+        const Layer L = P.prog[l];
+        if (L.kind == K_L0) {
+          // ---- layer 0 on CUDA cores (K = 3 after folding the latent into table.w) -> shared-memory activations
+          tc::epi_bar();
+          {
+            const float4* t = P.tables + L.slot * 512;
+            sTab[et] = __ldg(t + et);
+            sTab[et + 256] = __ldg(t + et + 256);
+          }
+          tc::epi_bar();
+#pragma unroll 1
+          for (int j = 0; j < 4; j++) {
+            const int c = 2 * j + h;
+            unsigned long long m = 0ull;
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) {
+              float v[8];
+#pragma unroll
+              for (int f = 0; f < 8; f++) {
+                const float4 t = sTab[c * 64 + gq * 8 + f];
+                v[f] = tc::leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
+                m |= (unsigned long long)(v[f] > 0.f) << (gq * 8 + f);
+              }
+              tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_bf16x2(v[0], v[1]),
+                               ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+            }
+            mrow[(size_t)(L.mask_layer * 4 + j) * 256] = m;
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * j);
+          }
+          continue;
+        }
+        if (L.kind == K_HEAD_F || L.kind == K_HEAD_H) {
+          const uint32_t buf = acc_it & 1u;
+          ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l);
+          acc_it++;
+          ptx::tc_fence_after();
+          uint32_t r[8];
+          if (h == 0) {
+            ptx::tmem_ld8(tmem_lane + TM_ACC + buf * NCH, r);
+            ptx::tmem_wait_ld();
+          }
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
+          if (h == 0) {
+#pragma unroll
+            for (int i = 0; i < 5; i++) {
+              const float v = __uint_as_float(r[i]) + __ldg(P.bias + L.bias_off + i);
+              if (L.kind == K_HEAD_F) yc[i] = v;
+              else yt[i] = tc::leaky(v, slope);  // decoder :259-270
+            }
+          }
+          if (L.kind == K_HEAD_H) {
+            // ---- loss and d loss / d head pre-activations of this sample (reconstruct.py:166-192)
+            float gt[5] = {0, 0, 0, 0, 0};
+            float l3[3] = {0.f, 0.f, 0.f};
+            if (h == 0 && live) simt::loss_row(P.loss, yc, yt, s_gt, n_gt, gc, gt, l3);
+            if (h == 0) {
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                l3[0] += __shfl_xor_sync(0xffffffffu, l3[0], o);
+                l3[1] += __shfl_xor_sync(0xffffffffu, l3[1], o);
+                l3[2] += __shfl_xor_sync(0xffffffffu, l3[2], o);
+              }
+              if (lane < 3) atomicAdd(P.loss_acc + lane, lane == 0 ? l3[0] : (lane == 1 ? l3[1] : l3[2]));
+            }
+            // the hnet head read the shared-memory activations; its MMAs are complete (accumulator barrier above)
+            write_head_operand(gt);
+          }
+          continue;
+        }
+        // ---------------- GEMM layers with a 128-column chunk drain
+        const bool fwd = (L.kind == K_FWD || L.kind == K_FWD_XYZ);
+        if (fwd) {
+          tc::epi_bar();  // previous users of sBias / sTab are done
+          if (L.kind == K_FWD) {
+            reinterpret_cast<float2*>(sBias)[et] = __ldg(reinterpret_cast<const float2*>(P.bias + L.bias_off) + et);
+          } else {
+            const float4* t = P.tables + L.slot * 512;
+            sTab[et] = __ldg(t + et);
+            sTab[et + 256] = __ldg(t + et + 256);
+          }
+          tc::epi_bar();
+        }
+        auto drain = [&](auto kind_c, auto dst_c, int j) {
+          constexpr int KIND = decltype(kind_c)::value;
+          constexpr int DST = decltype(dst_c)::value;
+          const uint32_t buf = acc_it & 1u;
+          ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j);
+          acc_it++;
+          ptx::tc_fence_after();
+          uint32_t r[64];
+          ptx::tmem_ld64(tmem_lane + TM_ACC + buf * NCH + h * 64, r);
+          ptx::tmem_wait_ld();
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
+          const int col0 = j * NCH + h * 64;
+          const int c = 2 * j + h;
+          unsigned long long* mw = mrow + (size_t)(L.mask_layer * 4 + j) * 256;
+          unsigned long long m = 0ull;
+          if (KIND == K_BWD || KIND == K_BWD_SUM || KIND == K_SUM) m = *mw;
+          uint32_t pk[32];
+          float* vf = reinterpret_cast<float*>(r);  // fp32 results in place (column sums)
+#pragma unroll
+          for (int gq = 0; gq < 8; gq++) {
+            float v[8];
+            if (KIND == K_FWD_XYZ) {
+#pragma unroll
+              for (int f = 0; f < 8; f++) {
+                const float4 t = sTab[col0 + gq * 8 + f];
+                v[f] = tc::leaky(__uint_as_float(r[gq * 8 + f]) + fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
+              }
+            } else if (KIND == K_FWD) {
+              const float4 b0 = *reinterpret_cast<const float4*>(sBias + col0 + gq * 8);
+              const float4 b1 = *reinterpret_cast<const float4*>(sBias + col0 + gq * 8 + 4);
+              const uint64_t bb[4] = {ptx::pack_f32x2(b0.x, b0.y), ptx::pack_f32x2(b0.z, b0.w),
+                                      ptx::pack_f32x2(b1.x, b1.y), ptx::pack_f32x2(b1.z, b1.w)};
+#pragma unroll
+              for (int f = 0; f < 4; f++) {
+                const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                const uint64_t t = ptx::add_f32x2(acc, bb[f]);
+                const uint64_t u = ptx::mul_f32x2(t, slope2);
+                v[2 * f] = fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u));
+                v[2 * f + 1] = fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u));
+              }
+            } else {
+#pragma unroll
+              for (int f = 0; f < 8; f++) {
+                const float a = __uint_as_float(r[gq * 8 + f]);
+                v[f] = ((m >> (gq * 8 + f)) & 1ull) ? a : a * slope;  // LeakyReLU'(pre) from the recorded sign
+              }
+            }
+            if (KIND == K_FWD || KIND == K_FWD_XYZ) {
+#pragma unroll
+              for (int f = 0; f < 8; f++) m |= (unsigned long long)(v[f] > 0.f) << (gq * 8 + f);
+            }
+            if (KIND == K_BWD_SUM || KIND == K_SUM) {
+#pragma unroll
+              for (int f = 0; f < 8; f++) vf[gq * 8 + f] = v[f];
+            }
+            if (KIND != K_SUM) {
+#pragma unroll
+              for (int f = 0; f < 4; f++) pk[gq * 4 + f] = ptx::pack_bf16x2(v[2 * f], v[2 * f + 1]);
+              if (DST == 0)
+                tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), pk[gq * 4], pk[gq * 4 + 1], pk[gq * 4 + 2],
+                                 pk[gq * 4 + 3]);
+            }
+          }
+          if (KIND == K_FWD || KIND == K_FWD_XYZ) *mw = m;
+          if (KIND != K_SUM) {
+            if (DST == 0) {
+              ptx::fence_proxy_async_smem();
+            } else {
+              ptx::tmem_st32(tmem_lane + TM_A + (uint32_t)(c * (KCH / 2)), pk);
+              ptx::tmem_wait_st();
+              ptx::tc_fence_before();
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * (4 * DST + j));
+          }
+          if (KIND == K_BWD_SUM || KIND == K_SUM) {
+            // column sums over the tile's rows: warp transpose-reduce, then one atomic per column and warp
+            float lo[32], hi[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) { lo[i] = vf[i]; hi[i] = vf[32 + i]; }
+            const float s0 = warp_colsum32(lo, lane), s1 = warp_colsum32(hi, lane);
+            float* cs = P.colsum + L.slot * 512 + col0;
+            atomicAdd(cs + lane, s0);
+            atomicAdd(cs + 32 + lane, s1);
+          }
+        };
+        using I0 = std::integral_constant<int, 0>;
+        using I1 = std::integral_constant<int, 1>;
+        using KF = std::integral_constant<int, K_FWD>;
+        using KX = std::integral_constant<int, K_FWD_XYZ>;
+        using KB = std::integral_constant<int, K_BWD>;
+        using KBS = std::integral_constant<int, K_BWD_SUM>;
+        using KS = std::integral_constant<int, K_SUM>;
+        for (int j = 0; j < L.n_chunks; j++) {
+          switch (L.kind) {
+            case K_FWD: if (L.dst) drain(KF{}, I1{}, j); else drain(KF{}, I0{}, j); break;
+            case K_FWD_XYZ: if (L.dst) drain(KX{}, I1{}, j); else drain(KX{}, I0{}, j); break;
+            case K_BWD: if (L.dst) drain(KB{}, I1{}, j); else drain(KB{}, I0{}, j); break;
+            case K_BWD_SUM: if (L.dst) drain(KBS{}, I1{}, j); else drain(KBS{}, I0{}, j); break;
+            default: drain(KS{}, I0{}, j); break;
+          }
+        }
+        // the fnet head gradient goes into the shared-memory rows once their last readers (this layer's MMAs,
+        // complete with the accumulator barrier of its last chunk) are done
+        if (L.after) write_head_operand(gc);
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync();
+  if (warp == 1) ptx::tmem_dealloc2(tmem_base, 512);
+}
+
+}  // namespace lat2
+}  // namespace dj

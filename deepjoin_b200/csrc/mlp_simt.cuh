@@ -185,70 +185,80 @@ struct LossCfg {
   float inv_n;
 };
 
+// Loss of ONE sample and its gradient wrt the 2 x 5 head pre-activations (reconstruct.py:166-192):
+// yc = fnet head pre-activations, yt = hnet head outputs AFTER its LeakyReLU (decoder :259-270).
+// gc / gt: d loss / d (head pre-activations); l3 += (sdf, occ, normal) loss terms of this sample.
+__device__ __forceinline__ void loss_row(const LossCfg& L, const float (&yc)[5], const float (&yt)[5], float s,
+                                         const float (&n_gt)[3], float (&gc)[5], float (&gt)[5], float (&l3)[3]) {
+  const float c_sdf = tanhf(yc[0]), t_sdf = tanhf(yt[0]);
+  const float sc = sigmoidf_(yc[1]), st = sigmoidf_(yt[1]);
+  float cn[3], tn[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) { cn[i] = tanhf(yc[2 + i]); tn[i] = tanhf(yt[2 + i]); }
+  const bool sel_b = (st > 0.5f) || (c_sdf < -t_sdf);
+  const float b_sdf = sel_b ? -t_sdf : c_sdf;
+  const float occ = (s <= 0.f) ? 1.f : 0.f;  // tensor_sdf_to_occ (core/reconstruct.py:33-34)
+  // sdf: lambda3 * mean |clamp(b_sdf) - s|
+  float d_bsdf = 0.f;
+  if (L.lambda3 != 0.f) {
+    const float cl = fminf(fmaxf(b_sdf, -L.clamp_dist), L.clamp_dist);
+    const float diff = cl - s;
+    l3[0] += L.lambda3 * L.inv_n * fabsf(diff);
+    const float sg = (diff > 0.f) ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    const bool pass = (b_sdf >= -L.clamp_dist) && (b_sdf <= L.clamp_dist);  // torch.clamp backward: closed interval
+    d_bsdf = pass ? L.lambda3 * L.inv_n * sg : 0.f;
+  }
+  // occ: BCELoss(b_occ, occ); log clamped at -100, backward (p - o) / max(p (1-p), 1e-12)
+  const float p = sc * (1.f - st);
+  {
+    const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
+    l3[1] += -L.inv_n * (occ * lp + (1.f - occ) * l1p);
+  }
+  const float d_p = L.inv_n * (p - occ) / fmaxf(p * (1.f - p), 1e-12f);
+  // normals: lambda1 * mean over 3N of (b_n - m)^2
+  float d_bn[3] = {0, 0, 0};
+  if (L.lambda1 != 0.f) {
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      const float bn = sel_b ? tn[i] : cn[i];
+      const float diff = bn - n_gt[i];
+      l3[2] += L.lambda1 * L.inv_n * (1.f / 3.f) * diff * diff;
+      d_bn[i] = L.lambda1 * L.inv_n * (2.f / 3.f) * diff;
+    }
+  }
+  // route through the select and the head non-linearities
+  gc[0] = (sel_b ? 0.f : d_bsdf) * (1.f - c_sdf * c_sdf);
+  gt[0] = (sel_b ? -d_bsdf : 0.f) * (1.f - t_sdf * t_sdf);
+  gc[1] = d_p * (1.f - st) * sc * (1.f - sc);
+  gt[1] = -d_p * sc * st * (1.f - st);
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    gc[2 + i] = (sel_b ? 0.f : d_bn[i]) * (1.f - cn[i] * cn[i]);
+    gt[2 + i] = (sel_b ? d_bn[i] : 0.f) * (1.f - tn[i] * tn[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < 5; i++) gt[i] *= (yt[i] > 0.f ? 1.f : L.slope);  // LeakyReLU on the hnet head (decoder :259-270)
+}
+
 __global__ void loss_grad_kernel(LossCfg L, const float* __restrict__ yC, const float* __restrict__ yT, int ld,
                                  const float* __restrict__ sdf_gt, const float* __restrict__ n_gt,
                                  float* __restrict__ dyC, float* __restrict__ dyT, float* __restrict__ loss_acc,
                                  int64_t n) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  float l_sdf = 0.f, l_occ = 0.f, l_n = 0.f;
+  float l3[3] = {0.f, 0.f, 0.f};
   if (g < n) {
-    float yc[5], yt[5];
+    float yc[5], yt[5], gc[5], gt[5];
 #pragma unroll
     for (int i = 0; i < 5; i++) { yc[i] = yC[g * ld + i]; yt[i] = yT[g * ld + i]; }
-    const float c_sdf = tanhf(yc[0]), t_sdf = tanhf(yt[0]);
-    const float sc = sigmoidf_(yc[1]), st = sigmoidf_(yt[1]);
-    float cn[3], tn[3];
-#pragma unroll
-    for (int i = 0; i < 3; i++) { cn[i] = tanhf(yc[2 + i]); tn[i] = tanhf(yt[2 + i]); }
-    const bool sel_b = (st > 0.5f) || (c_sdf < -t_sdf);
-    const float b_sdf = sel_b ? -t_sdf : c_sdf;
-    const float s = sdf_gt[g];
-    const float occ = (s <= 0.f) ? 1.f : 0.f;  // tensor_sdf_to_occ (core/reconstruct.py:33-34)
-    // sdf: lambda3 * mean |clamp(b_sdf) - s|
-    float d_bsdf = 0.f;
-    if (L.lambda3 != 0.f) {
-      const float cl = fminf(fmaxf(b_sdf, -L.clamp_dist), L.clamp_dist);
-      const float diff = cl - s;
-      l_sdf = L.lambda3 * L.inv_n * fabsf(diff);
-      const float sg = (diff > 0.f) ? 1.f : (diff < 0.f ? -1.f : 0.f);
-      const bool pass = (b_sdf >= -L.clamp_dist) && (b_sdf <= L.clamp_dist);  // torch.clamp backward: closed interval
-      d_bsdf = pass ? L.lambda3 * L.inv_n * sg : 0.f;
-    }
-    // occ: BCELoss(b_occ, occ); log clamped at -100, backward (p - o) / max(p (1-p), 1e-12)
-    const float p = sc * (1.f - st);
-    {
-      const float lp = fmaxf(logf(p), -100.f), l1p = fmaxf(logf(1.f - p), -100.f);
-      l_occ = -L.inv_n * (occ * lp + (1.f - occ) * l1p);
-    }
-    const float d_p = L.inv_n * (p - occ) / fmaxf(p * (1.f - p), 1e-12f);
-    // normals: lambda1 * mean over 3N of (b_n - m)^2
-    float d_bn[3] = {0, 0, 0};
-    if (L.lambda1 != 0.f) {
-#pragma unroll
-      for (int i = 0; i < 3; i++) {
-        const float bn = sel_b ? tn[i] : cn[i];
-        const float diff = bn - n_gt[3 * g + i];
-        l_n += L.lambda1 * L.inv_n * (1.f / 3.f) * diff * diff;
-        d_bn[i] = L.lambda1 * L.inv_n * (2.f / 3.f) * diff;
-      }
-    }
-    // route through the select and the head non-linearities
-    float gc[5], gt[5];
-    gc[0] = (sel_b ? 0.f : d_bsdf) * (1.f - c_sdf * c_sdf);
-    gt[0] = (sel_b ? -d_bsdf : 0.f) * (1.f - t_sdf * t_sdf);
-    gc[1] = d_p * (1.f - st) * sc * (1.f - sc);
-    gt[1] = -d_p * sc * st * (1.f - st);
-#pragma unroll
-    for (int i = 0; i < 3; i++) {
-      gc[2 + i] = (sel_b ? 0.f : d_bn[i]) * (1.f - cn[i] * cn[i]);
-      gt[2 + i] = (sel_b ? d_bn[i] : 0.f) * (1.f - tn[i] * tn[i]);
-    }
+    const float m[3] = {n_gt[3 * g], n_gt[3 * g + 1], n_gt[3 * g + 2]};
+    loss_row(L, yc, yt, sdf_gt[g], m, gc, gt, l3);
 #pragma unroll
     for (int i = 0; i < 5; i++) {
       dyC[g * ld + i] = gc[i];
-      dyT[g * ld + i] = gt[i] * (yt[i] > 0.f ? 1.f : L.slope);  // LeakyReLU on the hnet head (decoder :259-270)
+      dyT[g * ld + i] = gt[i];
     }
   }
+  float l_sdf = l3[0], l_occ = l3[1], l_n = l3[2];
   // block reduction -> 3 atomics per block
   __shared__ float red[3][8];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

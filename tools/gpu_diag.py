@@ -152,6 +152,70 @@ def stage_timing():
     return res
 
 
+def stage_latent_tc():
+    """Tensor-core fused forward+backward (latent_tc2.cuh) against the fp32 path and the autograd oracle."""
+    import numpy as np
+    import torch
+    from oracle import decoder_oracle as O, synth
+    from tests import util
+    from deepjoin_b200 import reconstruct as RR
+    res = {}
+    xyz, sdf, nrm = synth.make_sample_set(40000, seed=1)
+    for kind in ("default", "trained_norm"):
+        for n in (100, 1000, 30000):
+            x = torch.from_numpy(xyz[:n].astype(np.float32)).cuda()
+            s = torch.from_numpy(sdf[:n].astype(np.float32)).cuda()
+            m = torch.from_numpy(nrm[:n].astype(np.float32)).cuda()
+            dec = util.make_decoder(0, kind, precision="fp32")
+            code = util.code_for(0, kind)
+            g32, t32 = RR.latent_grad(dec, code.cuda(), x, s, m, precision="fp32")
+            g16, t16 = RR.latent_grad(dec, code.cuda(), x, s, m, precision="bf16")
+            torch.cuda.synchronize()
+            g32, g16 = g32.cpu().double(), g16.cpu().double()
+            r = {"rel_err_vs_fp32": float((g16 - g32).abs().max() / g32.abs().max()),
+                 "cos": float((g16 * g32).sum() / (g16.norm() * g32.norm())),
+                 "nan": int(torch.isnan(g16).sum()), "gnorm32": float(g32.norm()), "gnorm16": float(g16.norm()),
+                 "terms32": [float(v) for v in t32.cpu()], "terms16": [float(v) for v in t16.cpu()]}
+            if n <= 1000:
+                gr, tr = O.latent_grad(util.oracle_net(0, kind), code, x.cpu(), s.cpu(), m.cpu())
+                r["rel_err_vs_oracle"] = float((g16 - gr.double()).abs().max() / gr.abs().max())
+            res["%s_n%d" % (kind, n)] = r
+    return res
+
+
+def stage_latent_timing():
+    """Config 3 per-shape cost: 30,000 samples / iteration, device-resident loop (dj_latent_optimize)."""
+    import numpy as np
+    import torch
+    from oracle import synth
+    from tests import util
+    from deepjoin_b200 import reconstruct as RR
+    xyz, sdf, nrm = synth.make_sample_set(200000, seed=1)
+    dec = util.make_decoder(0, "trained_norm", precision="fp32")
+    lat_prec = os.environ.get("LATENT_PRECISION", "fp32")
+    dev = torch.device("cuda", 0)
+    px = torch.from_numpy(xyz.astype(np.float32)).to(dev)
+    ps = torch.from_numpy(sdf.astype(np.float32).reshape(-1)).to(dev)
+    pn = torch.from_numpy(nrm.astype(np.float32)).to(dev)
+    res = {}
+    for iters, ns in ((20, 30000), (100, 30000), (100, 8000)):
+        sched = torch.randint(0, px.shape[0], (iters, ns), device=dev, dtype=torch.int32)
+        code0 = RR.init_code(128, 64, 0.01)
+        RR.optimize_code(dec, code0, px, ps, pn, sched[:2], 5e-3, 1.0, 1.0, 0.1, l2reg=True, precision=lat_prec)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        log, code = RR.optimize_code(dec, code0, px, ps, pn, sched, 5e-3, 1.0, 1.0, 0.1, l2reg=True, precision=lat_prec)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        res["it%d_n%d" % (iters, ns)] = {"ms_per_iter": ms / iters, "wall_ms_per_iter": 1e3 * (time.time() - t0) / iters,
+                                         "tflops_alg": ns * 11.03e6 / (ms / iters * 1e-3) / 1e12,
+                                         "loss_first_last": [float(log[0, 1]), float(log[-1, 1])]}
+    return res
+
+
 def stage_prof():
     """In-kernel cycle counters of the CTA-pair forward (DEEPJOIN_B200_DEBUG |= 8): where each warp role waits."""
     import numpy as np
@@ -186,7 +250,7 @@ def stage_prof():
     return out
 
 
-STAGES = {"prof": stage_prof, "probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
+STAGES = {"prof": stage_prof, "latent_timing": stage_latent_timing, "latent_tc": stage_latent_tc, "probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
           "timing": stage_timing}
 
 if __name__ == "__main__":
