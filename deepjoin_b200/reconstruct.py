@@ -8,7 +8,11 @@ stream (numpy global RNG consumed exactly like core/data.py does), but the 800-i
 -- batch gather, forward, clamped-L1 + BCE + normal loss, backward to the code only, Adam, lr
 step, loss logging every 10th iteration -- runs on the device without host round trips
 (dj_latent_optimize).  ``sampling_method="device"`` (extension) also draws the schedule on the
-device (dj_sample_schedule), removing the reference's ~60 ms/iteration of host sampling."""
+device (dj_sample_schedule), removing the reference's ~60 ms/iteration of host sampling.
+
+Arithmetic follows ``decoder.precision`` (override: ``decoder.latent_precision``): "bf16" runs one fused
+forward + loss + backward tensor-core kernel per iteration (csrc/latent_tc2.cuh; gradient with bf16
+rounding noise, ~1e-2 relative), "fp32" the reference's arithmetic on CUDA cores."""
 from collections import defaultdict
 
 import numpy as np
@@ -111,7 +115,7 @@ def reconstruct(decoder, num_iterations, latent_size, break_latent_size, test_sd
 
     log, code = optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, sched, lr, lambda1, lambda3, clamp_dist,
                               l2reg=l2reg, code_reg_lambda=code_reg_lambda, log_every=10,
-                              precision=getattr(decoder, "latent_precision", "fp32"))
+                              precision=getattr(decoder, "latent_precision", None) or getattr(decoder, "precision", "bf16"))
     log = log.cpu().numpy()
     loss_dict = defaultdict(lambda: [])
     for row in log:

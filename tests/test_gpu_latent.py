@@ -132,3 +132,82 @@ def idx_dev_ptr():
     t = torch.empty(4096, dtype=torch.int32, device="cuda")
     idx_dev_ptr.keep = t
     return t.data_ptr()
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core latent step (csrc/latent_tc2.cuh): bf16 operands, fp32 accumulation.  Tolerances: the
+# gradient carries bf16 rounding noise (north_star: fp32-accumulated bf16), loss terms are those of the
+# bf16 forward.
+# ---------------------------------------------------------------------------------------------
+def _cos(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return float((a * b).sum() / (a.norm() * b.norm()))
+
+
+@pytest.mark.parametrize("kind,tol_g,tol_l", [("default", 3e-2, 1e-4), ("trained_norm", 6e-2, 2e-2)])
+@pytest.mark.parametrize("n", [1, 100, 777, 4000])
+def test_tensor_core_latent_gradient_vs_autograd(kind, tol_g, tol_l, n):
+    from deepjoin_b200 import reconstruct as R
+    dec = util.make_decoder(0, kind, precision="bf16")
+    net = util.oracle_net(0, kind)
+    xyz, sdf, nrm = synth.make_sample_set(8000, seed=1)
+    idx = np.random.default_rng(n).permutation(8000)[:n]
+    x, s, m = (torch.from_numpy(a[idx].astype(np.float32)) for a in (xyz, sdf, nrm))
+    code = util.code_for(0, kind)
+    ref, t = O.latent_grad(net, code, x, s, m)
+    grad, terms = R.latent_grad(dec, code.cuda(), x.cuda(), s.cuda(), m.cuda(), precision="bf16")
+    grad = grad.cpu()
+    assert torch.isfinite(grad).all()
+    if n >= 100:
+        assert _cos(grad, ref) > 0.998
+        # few samples: less averaging of the bf16 rounding noise
+        assert float((grad - ref).abs().max()) <= tol_g * (3.0 if n < 1000 else 1.0) * float(ref.abs().max())
+    assert np.allclose(terms.cpu().numpy(), np.asarray(t), rtol=tol_l, atol=tol_l)
+
+
+def test_tensor_core_latent_gradient_options_and_multi_pass():
+    """Loss switches, and a batch larger than one pass of the grid (148 CTAs x 128 rows)."""
+    from deepjoin_b200 import reconstruct as R
+    dec = util.make_decoder(1, "trained_norm", precision="bf16")
+    net = util.oracle_net(1, "trained_norm")
+    xyz, sdf, nrm = synth.make_sample_set(40000, seed=1)
+    code = util.trained_code(1)
+    for n, kw in ((777, dict(lambda1=0.0)), (777, dict(lambda3=0.0)), (777, dict(l2reg=False)), (777, dict(clamp_dist=0.03)),
+                  (30000, dict(lambda1=0.5, lambda3=2.0))):
+        x, s, m = (torch.from_numpy(a[:n].astype(np.float32)) for a in (xyz, sdf, nrm))
+        ref, t = O.latent_grad(net, code, x, s, m, **kw)
+        grad, terms = R.latent_grad(dec, code.cuda(), x.cuda(), s.cuda(), m.cuda(), precision="bf16", **kw)
+        assert _cos(grad.cpu(), ref) > 0.998, kw
+        assert float((grad.cpu() - ref).abs().max()) <= 6e-2 * float(ref.abs().max()), kw
+        assert np.allclose(terms.cpu().numpy(), np.asarray(t), rtol=2e-2, atol=2e-2), kw
+
+
+def test_tensor_core_adam_loop_tracks_the_fp32_loop():
+    """Same schedule, same start: the bf16 loop's loss curve and final code stay close to the fp32 loop's
+    (in-kernel gather of the mini-batch rows vs the fp32 path's gather kernel)."""
+    from deepjoin_b200 import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision="fp32")
+    xyz, sdf, nrm = synth.make_sample_set(20000, seed=2)
+    px, ps, pn = (torch.from_numpy(a.astype(np.float32)).cuda() for a in (xyz, sdf.reshape(-1), nrm))
+    sched = torch.from_numpy(np.random.default_rng(0).integers(0, 20000, (80, 3000)).astype(np.int32)).cuda()
+    code0 = R.init_code(128, 64, 0.01)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        log, code = R.optimize_code(dec, code0, px, ps, pn, sched, lr=5e-3, lambda1=1.0, lambda3=1.0, clamp_dist=0.1,
+                                    l2reg=True, precision=prec)
+        out[prec] = (log.cpu().numpy(), code.cpu().numpy())
+    l32, l16 = out["fp32"][0][:, 1], out["bf16"][0][:, 1]
+    assert l16[-1] < l16[0] and np.abs(l16 - l32).max() < 0.05 * np.abs(l32).max()
+    assert np.abs(out["bf16"][1] - out["fp32"][1]).max() < 0.05 * np.abs(out["fp32"][1]).max() + 2e-2
+
+
+def test_reconstruct_follows_decoder_precision():
+    from deepjoin_b200.reconstruct import reconstruct
+    dec = util.make_decoder(0, "trained_norm", precision="bf16")
+    xyz, sdf, nrm = synth.make_sample_set(20000, seed=2)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    loss, code = reconstruct(dec, 40, 128, 64, [xyz, sdf, nrm], 0.01, 1.0, 0.0, 1.0, 0.1, num_samples=2000, lr=5e-3,
+                             l2reg=True, sampling_method="device")
+    assert loss["epoch"] == [0, 10, 20, 30] and loss["loss"][-1] < loss["loss"][0]
+    assert torch.isfinite(code).all()
