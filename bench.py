@@ -78,17 +78,37 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+SPECS = {  # experiments/mugs/specs.json of the reference
+    "NetworkSpecs": {"dims": [512] * 8, "dropout": list(range(8)), "dropout_prob": 0.2, "norm_layers": list(range(8)),
+                     "latent_in": [4], "xyz_in_all": False, "use_tanh": False, "latent_dropout": False,
+                     "weight_norm": True},
+    "SubnetSpecs": {"subnet_dims": [512] * 5, "subnet_dropout": list(range(5)), "subnet_norm": list(range(5)),
+                    "subnet_xyz": True},
+}
+
+
+def make_decoder(seed, device, precision):
+    """Product decoder with synthetic trained-norm weights (synth_data.py; no oracle code involved)."""
+    import synth_data
+    from deepjoin_b200.networks.decoder_z_lb_both_leaky_n_sdf import Decoder
+    dec = Decoder(latent_size=128, tool_latent_size=64, num_dims=3, do_code_regularization=True,
+                  **SPECS["NetworkSpecs"], **SPECS["SubnetSpecs"])
+    dec.load_state_dict(synth_data.make_state_dict(seed, "trained_norm"))
+    dec.precision = precision
+    return dec.to(device).eval()
+
+
 def cpu_decoder_rate(n_points, use_net=1, threads=None):
-    """Oracle port of the reference decoder (torch fp32 on the host cores)."""
+    """THE ONLY PLACE bench.py touches oracle/: the oracle port of the reference decoder (torch fp32 on the
+    host cores), timed as the CPU baseline / reference arm."""
     import torch
+    import synth_data
     from oracle import decoder_oracle as O
-    from tests import util
     if threads:
         torch.set_num_threads(threads)
-    net = util.oracle_net(0, "trained_norm")
-    code = util.trained_code(0)
-    from oracle import synth
-    pts = synth.make_points(min(n_points, 1 << 16), 0)
+    net = O.fold(synth_data.make_state_dict(0, "trained_norm"), dtype=torch.float32)
+    code = synth_data.trained_code(0)
+    pts = synth_data.make_points(min(n_points, 1 << 16), 0)
     with torch.no_grad():
         O.forward(net, code, pts[:4096], use_net)  # warm-up
         done, t0 = 0, time.perf_counter()
@@ -141,6 +161,9 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--query-only", action="store_true", help="diagnostics: time the grid query alone (not a bench line)")
+    ap.add_argument("--latent-shapes", type=int, default=8,
+                    help="shapes per GPU of the second half of the metric (BASELINE configs[2]: 800 Adam iterations x 30,000 "
+                         "samples per shape, then one 256^3 restoration mesh); 0 disables")
     ap.add_argument("--slab-dims", type=int, default=0,
                     help="also time BASELINE configs[3]: ONE grid of this size sharded by axis-0 slabs over the ranks, "
                          "fragments gathered to rank 0 over NCCL (adds a 'slab' object to the JSON line)")
@@ -152,8 +175,8 @@ def main():
     import torch
     import torch.distributed as dist
     from deepjoin_b200 import _lib
+    import synth_data
     from deepjoin_b200.core import reconstruct as R
-    from tests import util
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -172,8 +195,8 @@ def main():
     dims = (d, d, d)
     npts = d ** 3
     u = args.use_net
-    dec = util.make_decoder(rank % 2, "trained_norm", device=dev, precision=args.precision)
-    code = util.trained_code(rank)
+    dec = make_decoder(rank % 2, dev, args.precision)
+    code = synth_data.trained_code(rank)
     code_dev = code.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -232,12 +255,58 @@ def main():
     e2e_ms = 1e3 * (time.perf_counter() - w0)
     clocks = sampler.stop() if sampler else None
 
+    latent = None
+    if args.latent_shapes and not args.query_only:
+        from deepjoin_b200 import reconstruct as RR
+        n_sh, iters_l, ns_l = args.latent_shapes, 800, 30000
+        xyz_s, sdf_s, nrm_s = synth_data.make_sample_set(100000, seed=rank)
+        px = torch.from_numpy(xyz_s.astype(np.float32)).to(dev)
+        ps = torch.from_numpy(sdf_s.astype(np.float32).reshape(-1)).to(dev)
+        pn = torch.from_numpy(nrm_s.astype(np.float32)).to(dev)
+        sched = torch.empty((iters_l, ns_l), device=dev, dtype=torch.int32)
+
+        def one_shape(seed, n_it):
+            _lib.check(_lib.lib().dj_sample_schedule(ps.data_ptr(), ps.shape[0], n_it, ns_l, 0.2, 1000 + seed, sched.data_ptr(),
+                                                     _lib.stream_ptr()))
+            torch.manual_seed(seed)
+            log, c = RR.optimize_code(dec, RR.init_code(128, 64, 0.01), px, ps, pn, sched[:n_it], 5e-3, 1.0, 1.0, 0.1,
+                                      l2reg=True, code_reg_lambda=1e-4, precision=args.precision)
+            m = R.create_mesh(c, dec, 2, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
+            return log, m
+
+        try:
+            one_shape(0, 20)
+        except Exception:  # restoration surface may be empty for a barely optimised code: warm-up only
+            pass
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        wl = time.perf_counter()
+        l0.record()
+        n_mesh, last_loss = 0, None
+        for sh in range(n_sh):
+            try:
+                log, m = one_shape(rank * n_sh + sh, iters_l)
+                n_mesh += 1
+                last_loss = float(log[-1, 1])
+            except Exception as e:  # IsosurfaceExtractionError -> empty mesh, as the reference's mesh_chunk does
+                last_loss = None
+        l1.record()
+        torch.cuda.synchronize()
+        tl = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        if rank == 0:
+            latent = {"workload": "configs[2]: %d shapes per GPU x %d Adam iterations x %d samples (device sampler, fused "
+                                  "forward+backward tensor-core step), then one %d^3 restoration mesh per shape" % (n_sh, iters_l, ns_l, d),
+                      "shapes_per_s": world * n_sh / (float(tl[0]) * 1e-3), "ms_per_shape": float(tl[0]) / n_sh,
+                      "wall_ms_per_shape": 1e3 * (time.perf_counter() - wl) / n_sh, "meshes_with_surface": n_mesh,
+                      "final_loss_last_shape": last_loss, "precision": args.precision}
     slab = None
     if args.slab_dims:
         from deepjoin_b200 import parallel as Par
         sd = (args.slab_dims,) * 3
-        dec0 = util.make_decoder(0, "trained_norm", device=dev, precision=args.precision)  # same weights on every rank
-        code0 = util.trained_code(0).to(dev)
+        dec0 = make_decoder(0, dev, args.precision)  # same weights on every rank
+        code0 = synth_data.trained_code(0).to(dev)
         for _ in range(2):
             m = Par.create_mesh_sharded(code0, dec0, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=sd, padding=0.1)
         barrier()
@@ -287,6 +356,8 @@ def main():
                          "flop_per_query": FLOP_ALG[u]},
             "clocks": clocks,
         }
+        if latent:
+            line["latent"] = latent
         if slab:
             line["slab"] = slab
         if not args.no_cpu_baseline and world == 1:

@@ -166,3 +166,42 @@ def test_dropin_import_names():
     env = dict(os.environ, PYTHONPATH=ROOT + os.pathsep + os.path.join(ROOT, "deepjoin_b200", "dropin"))
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr
+
+
+def test_bench_own_arm_does_not_touch_the_oracle():
+    """bench.py may execute oracle/ only in its cpu_baseline / --impl reference leg (cpu_decoder_rate)."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef):
+            for sub in ast.walk(node):
+                names = []
+                if isinstance(sub, ast.ImportFrom):
+                    names = [sub.module or ""]
+                elif isinstance(sub, ast.Import):
+                    names = [a.name for a in sub.names]
+                for nm in names:
+                    if nm.split(".")[0] in ("oracle", "tests"):
+                        assert node.name == "cpu_decoder_rate", (node.name, nm)
+    for node in tree.body:  # module level
+        if isinstance(node, (ast.Import, ast.ImportFrom)):
+            nm = getattr(node, "module", None) or node.names[0].name
+            assert nm.split(".")[0] not in ("oracle", "tests")
+    # the synthetic-input module is oracle-free
+    sd = open(os.path.join(ROOT, "synth_data.py")).read()
+    assert not re.search(r"^\s*(from|import)\s+(oracle|tests)\b", sd, flags=re.M)
+
+
+def test_synthetic_weights_do_not_need_the_oracle():
+    """synth_data (committed head shifts) and oracle.synth (fp64 oracle centring) build identical weights."""
+    import torch
+    import synth_data
+    from oracle import synth
+    a = synth_data.make_state_dict(3, "trained_norm")
+    shifts = synth.compute_head_shifts({k: v.clone() for k, v in synth_data.make_state_dict(3, "default").items()}, synth.MUGS, 3)
+    assert len(shifts) == 2
+    b = synth.make_state_dict(3, "trained_norm")
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    c = synth.make_state_dict(11, "trained_norm")  # no committed shift -> oracle centring
+    assert set(c) == set(a)
