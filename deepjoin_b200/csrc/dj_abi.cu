@@ -843,6 +843,7 @@ struct DjMcWork {
   DevBuf var, counts, offs, edge, misc, verts, faces, merge;
   double* v64 = nullptr;  // create_mesh: final float64 vertices on the device (inside verts / merge)
   int64_t nblocks = 0, nv = 0, nf = 0;
+  int bpp = 0;  // blocks per cell layer (grid.x of the marching-cubes kernels; grid.y = cell layers)
   const float* vol = nullptr;
   bool counted = false;
   // create_mesh post-processing
@@ -880,23 +881,30 @@ extern "C" int dj_mc_count(DjMcWork* w, const float* vol_dev, int n0, int n1, in
   D.ncells = (int64_t)(n0 - 1) * D.c1 * D.c2;
   D.level = level;
   w->vol = vol_dev;
-  w->nblocks = (D.ncells + mc::CB - 1) / mc::CB;
+  if (n0 - 1 > 65535) return fail(DJ_ERR_UNSUPPORTED, "dj_mc_count: more than 65535 cell layers");
+  w->bpp = (int)(((int64_t)D.c1 * D.c2 + mc::CB - 1) / mc::CB);
+  w->nblocks = (int64_t)(n0 - 1) * w->bpp;
   const int64_t nsamp = (int64_t)n0 * n1 * n2;
   DJ_CUDA(w->var.reserve((size_t)D.ncells * sizeof(uint16_t)));
   DJ_CUDA(w->counts.reserve((size_t)w->nblocks * sizeof(int2)));
   DJ_CUDA(w->offs.reserve((size_t)w->nblocks * sizeof(int2)));
-  DJ_CUDA(w->misc.reserve(64));
+  const int64_t ngroups = (w->nblocks + mc::SG - 1) / mc::SG;
+  DJ_CUDA(w->misc.reserve(64 + (size_t)ngroups * sizeof(longlong2)));
   long long* totals = w->misc.as<long long>();
   int* mm = reinterpret_cast<int*>(totals + 2);
+  longlong2* group_off = reinterpret_cast<longlong2*>(totals + 8);
   if (check_range) {
     const int init[2] = {0x7FFFFFFF, (int)0x80000000};
     DJ_CUDA(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st));
     mc::minmax_kernel<<<1184, 256, 0, st>>>(vol_dev, nsamp, mm);
     DJ_LAUNCHED();
   }
-  mc::classify_kernel<<<(unsigned)w->nblocks, mc::CB, 0, st>>>(D, vol_dev, w->var.as<uint16_t>(), w->counts.as<int2>());
+  const dim3 mc_grid((unsigned)w->bpp, (unsigned)(n0 - 1));
+  mc::classify_kernel<<<mc_grid, mc::CB, 0, st>>>(D, vol_dev, w->var.as<uint16_t>(), w->counts.as<int2>());
   DJ_LAUNCHED();
-  mc::scan_blocks_kernel<<<1, 1024, 0, st>>>(w->counts.as<int2>(), w->nblocks, w->offs.as<int2>(), totals);
+  mc::scan_groups_kernel<<<(unsigned)ngroups, mc::SG, 0, st>>>(w->counts.as<int2>(), w->nblocks, w->offs.as<int2>(), group_off);
+  DJ_LAUNCHED();
+  mc::scan_totals_kernel<<<1, mc::SG, 0, st>>>(group_off, ngroups, totals);
   DJ_LAUNCHED();
   long long h[3];
   DJ_CUDA(cudaMemcpyAsync(h, totals, sizeof h, cudaMemcpyDeviceToHost, st));
@@ -932,9 +940,11 @@ extern "C" int dj_mc_fill(DjMcWork* w, int descent, float* verts_dev, int32_t* f
     mc::seam_fill_kernel<<<ceil_div(np * 2, 256), 256, 0, st>>>(w->edge.as<int>(), np);
     DJ_LAUNCHED();
   }
-  mc::emit_vertices_kernel<<<(unsigned)w->nblocks, mc::CB, 0, st>>>(D, w->vol, w->var.as<uint16_t>(), w->offs.as<int2>(), w->edge.as<int>(), verts_dev);
+  const dim3 mc_grid((unsigned)w->bpp, (unsigned)(D.n0 - 1));
+  const longlong2* group_off = reinterpret_cast<const longlong2*>(w->misc.as<long long>() + 8);
+  mc::emit_vertices_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->vol, w->var.as<uint16_t>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), verts_dev);
   DJ_LAUNCHED();
-  mc::emit_faces_kernel<<<(unsigned)w->nblocks, mc::CB, 0, st>>>(D, w->var.as<uint16_t>(), w->offs.as<int2>(), w->edge.as<int>(), descent, faces_dev);
+  mc::emit_faces_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->var.as<uint16_t>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), descent, faces_dev);
   DJ_LAUNCHED();
   return DJ_OK;
 }

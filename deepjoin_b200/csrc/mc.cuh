@@ -9,8 +9,13 @@
 //     edge among the cell's owned edges in first-appearance order of its triangle list;
 //   * face offset = exclusive scan of triangle counts.
 // Kernels: classify (cube index + asymptotic-decider variant, per-block counts, warp-shuffle
-// reduction) -> block scan -> emit vertices (+ edge->id table) -> emit faces.  HBM-bound:
-// 4 B/sample read by classify; the emit passes stream the 2 B/cell variant array.
+// reduction) -> two-level scan of the block counts -> emit vertices (+ edge->id table) -> emit faces.
+// A block owns 256 consecutive cells of one cell layer (blockIdx.y = layer, so the sweep-order block
+// index needs no 64-bit division).  Only ~3 % of the cells are cut by the surface: the emit kernels
+// compact the block's owned vertices / triangles into shared memory with the block scan and then give
+// every thread ONE vertex (one inverse-distance interpolation in float64) or ONE triangle, instead of
+// one cell with up to 13 vertices.  HBM-bound: 4 B/sample read by classify; the emit passes stream the
+// 2 B/cell variant array.
 #pragma once
 #include "common.cuh"
 
@@ -34,12 +39,17 @@ struct Dims {
   double level;
 };
 
-__device__ __forceinline__ void cell_coords(const Dims& D, int64_t ci, int& zr, int& y, int& x) {
-  x = (int)(ci % D.c2);
-  const int64_t q = ci / D.c2;
-  y = (int)(q % D.c1);
-  zr = (int)(q / D.c1);
+// block -> cells: blockIdx.y = cell layer zr, blockIdx.x*CB + threadIdx.x = cell within the layer (row-major y, x)
+__device__ __forceinline__ bool block_cell(const Dims& D, int t, int& zr, int& y, int& x, int64_t& ci) {
+  zr = (int)blockIdx.y;
+  const unsigned idx = blockIdx.x * (unsigned)CB + (unsigned)t;
+  const unsigned plane = (unsigned)D.c1 * (unsigned)D.c2;
+  y = (int)(idx / (unsigned)D.c2);
+  x = (int)(idx - (unsigned)y * (unsigned)D.c2);
+  ci = (int64_t)zr * plane + idx;
+  return idx < plane;
 }
+__device__ __forceinline__ int64_t block_linear() { return (int64_t)blockIdx.y * gridDim.x + blockIdx.x; }
 
 __device__ __forceinline__ void load_cube(const Dims& D, const float* __restrict__ vol, int zr, int y, int x, double (&f)[8]) {
   const int z = zr;
@@ -129,11 +139,10 @@ __global__ void minmax_kernel(const float* __restrict__ vol, int64_t n, int* __r
 __global__ void __launch_bounds__(CB) classify_kernel(Dims D, const float* __restrict__ vol, uint16_t* __restrict__ var_out,
                                                       int2* __restrict__ block_counts) {
   __shared__ int red[2][CB / 32];
-  const int64_t ci = (int64_t)blockIdx.x * CB + threadIdx.x;
+  int zr, y, x;
+  int64_t ci;
   int nv = 0, nt = 0;
-  if (ci < D.ncells) {
-    int zr, y, x;
-    cell_coords(D, ci, zr, y, x);
+  if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
     double f[8];
     load_cube(D, vol, zr, y, x, f);
     const int var = cube_variant(f);
@@ -152,45 +161,63 @@ __global__ void __launch_bounds__(CB) classify_kernel(Dims D, const float* __res
   if (threadIdx.x == 0) {
     int a = 0, b = 0;
     for (int i = 0; i < CB / 32; i++) { a += red[0][i]; b += red[1][i]; }
-    block_counts[blockIdx.x] = make_int2(a, b);
+    block_counts[block_linear()] = make_int2(a, b);
   }
 }
 
-// ---- pass 2: exclusive scan of the per-block counts (single CTA), totals for the host
-__global__ void __launch_bounds__(1024) scan_blocks_kernel(const int2* __restrict__ counts, int64_t nblocks,
-                                                           int2* __restrict__ offsets, long long* __restrict__ totals) {
+// ---- pass 2: exclusive scan of the per-block counts in two levels.
+// level 1: every CTA scans 1024 counts in place (-> offsets within its group) and writes the group total;
+// level 2: one CTA scans the group totals and writes the grand totals for the host.  Consumers add
+// offsets[b] + group_off[b >> 10].
+constexpr int SG = 1024;
+__device__ __forceinline__ void scan1024(long long& a, long long& b, long long (*wsum)[32]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const long long a0 = a, b0 = b;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const long long ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
+    if (lane >= o) { a += ta; b += tb; }
+  }
+  if (lane == 31) { wsum[0][w] = a; wsum[1][w] = b; }
+  __syncthreads();
+  if (w == 0) {
+    long long sa = wsum[0][lane], sb = wsum[1][lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
+      if (lane >= o) { sa += ta; sb += tb; }
+    }
+    wsum[0][lane] = sa;
+    wsum[1][lane] = sb;
+  }
+  __syncthreads();
+  a = (w ? wsum[0][w - 1] : 0) + a - a0;  // exclusive
+  b = (w ? wsum[1][w - 1] : 0) + b - b0;
+}
+__global__ void __launch_bounds__(SG) scan_groups_kernel(const int2* __restrict__ counts, int64_t nblocks, int2* __restrict__ offsets,
+                                                         longlong2* __restrict__ group_tot) {
+  __shared__ long long wsum[2][32];
+  const int64_t i = (int64_t)blockIdx.x * SG + threadIdx.x;
+  const int2 c = (i < nblocks) ? counts[i] : make_int2(0, 0);
+  long long a = c.x, b = c.y;
+  scan1024(a, b, wsum);
+  if (i < nblocks) offsets[i] = make_int2((int)a, (int)b);
+  if (threadIdx.x == SG - 1) group_tot[blockIdx.x] = make_longlong2(a + c.x, b + c.y);
+}
+__global__ void __launch_bounds__(SG) scan_totals_kernel(longlong2* __restrict__ group_tot, int64_t ngroups,
+                                                         long long* __restrict__ totals) {
   __shared__ long long wsum[2][32];
   __shared__ long long carry[2];
   if (threadIdx.x == 0) { carry[0] = 0; carry[1] = 0; }
   __syncthreads();
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int64_t base = 0; base < nblocks; base += 1024) {
+  for (int64_t base = 0; base < ngroups; base += SG) {
     const int64_t i = base + threadIdx.x;
-    const int2 c = (i < nblocks) ? counts[i] : make_int2(0, 0);
+    const longlong2 c = (i < ngroups) ? group_tot[i] : make_longlong2(0, 0);
     long long a = c.x, b = c.y;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const long long ta = __shfl_up_sync(0xffffffffu, a, o), tb = __shfl_up_sync(0xffffffffu, b, o);
-      if (lane >= o) { a += ta; b += tb; }
-    }
-    if (lane == 31) { wsum[0][w] = a; wsum[1][w] = b; }
+    scan1024(a, b, wsum);
+    if (i < ngroups) group_tot[i] = make_longlong2(carry[0] + a, carry[1] + b);
     __syncthreads();
-    if (w == 0) {
-      long long sa = wsum[0][lane], sb = wsum[1][lane];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const long long ta = __shfl_up_sync(0xffffffffu, sa, o), tb = __shfl_up_sync(0xffffffffu, sb, o);
-        if (lane >= o) { sa += ta; sb += tb; }
-      }
-      wsum[0][lane] = sa;
-      wsum[1][lane] = sb;
-    }
-    __syncthreads();
-    const long long pa = carry[0] + (w ? wsum[0][w - 1] : 0) + a - c.x;
-    const long long pb = carry[1] + (w ? wsum[1][w - 1] : 0) + b - c.y;
-    if (i < nblocks) offsets[i] = make_int2((int)pa, (int)pb);
-    __syncthreads();
-    if (threadIdx.x == 0) { carry[0] += wsum[0][31]; carry[1] += wsum[1][31]; }
+    if (threadIdx.x == SG - 1) { carry[0] += a + c.x; carry[1] += b + c.y; }
     __syncthreads();
   }
   if (threadIdx.x == 0) { totals[0] = carry[0]; totals[1] = carry[1]; }
@@ -223,34 +250,48 @@ __device__ __forceinline__ void edge_frac(const double (&f)[8], int e, double (&
   }
 }
 
-// ---- pass 3: vertices (sweep first-use order) + edge -> id table
-__global__ void __launch_bounds__(CB) emit_vertices_kernel(Dims D, const float* __restrict__ vol,
-                                                           const uint16_t* __restrict__ var_in,
-                                                           const int2* __restrict__ block_off, int* __restrict__ edge_id,
-                                                           float* __restrict__ verts) {
+// ---- pass 3: vertices (sweep first-use order) + edge -> id table.  One thread per owned vertex.
+constexpr int MAXV = 13;  // owned vertices of one cell: 12 edges + the centre
+__global__ void __launch_bounds__(CB, 4) emit_vertices_kernel(Dims D, const float* __restrict__ vol,
+                                                              const uint16_t* __restrict__ var_in,
+                                                              const int2* __restrict__ block_off,
+                                                              const longlong2* __restrict__ group_off, int* __restrict__ edge_id,
+                                                              float* __restrict__ verts) {
   __shared__ int sscan[CB / 32];
-  const int64_t ci = (int64_t)blockIdx.x * CB + threadIdx.x;
-  int var = 0, nv = 0, zr = 0, y = 0, x = 0;
+  __shared__ uint16_t slist[CB * MAXV];  // (cell's thread << 4) | edge, in id order
+  int zr, y, x;
+  int64_t ci;
+  int var = 0, nv = 0;
   unsigned own = 0;
-  if (ci < D.ncells) {
+  if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
     var = var_in[ci];
     if (DJ_MC_NTRI[var]) {
-      cell_coords(D, ci, zr, y, x);
       own = owned_mask(D, zr, y, x);
       nv = owned_count(var, own);
     }
   }
   int tot;
   const int pre = block_excl_scan(nv, sscan, &tot);
-  if (nv == 0) return;
-  int id = block_off[blockIdx.x].x + pre;
-  double f[8];
-  load_cube(D, vol, zr, y, x, f);
-  const int ne = DJ_MC_NEDGE[var];
-  const int base[3] = {x, y, D.z_off + zr};
-  for (int k = 0; k < ne; k++) {
-    const int e = DJ_MC_ORDER[var][k];
-    if (!((own >> e) & 1u)) continue;
+  if (tot == 0) return;
+  if (nv) {
+    const int ne = DJ_MC_NEDGE[var];
+    int r = pre;
+    for (int k = 0; k < ne; k++) {
+      const int e = DJ_MC_ORDER[var][k];
+      if ((own >> e) & 1u) slist[r++] = (uint16_t)((threadIdx.x << 4) | e);
+    }
+  }
+  __syncthreads();
+  const int64_t bl = block_linear();
+  const int64_t id0 = (int64_t)block_off[bl].x + group_off[bl >> 10].x;
+  for (int v = threadIdx.x; v < tot; v += CB) {
+    const int ent = slist[v];
+    const int e = ent & 15;
+    int cz, cy, cx;
+    int64_t cci;
+    block_cell(D, ent >> 4, cz, cy, cx, cci);
+    double f[8];
+    load_cube(D, vol, cz, cy, cx, f);
     double fr[3];
     if (e == 12) {
       // cell-centre vertex: mean of the cell's edge vertices, accumulated in edge-id order
@@ -270,14 +311,15 @@ __global__ void __launch_bounds__(CB) emit_vertices_kernel(Dims D, const float* 
     } else {
       edge_frac(f, e, fr);
     }
+    const int base[3] = {cx, cy, D.z_off + cz};
     float p[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) p[d] = (float)__dadd_rn((double)base[d], fr[d]);
-    verts[3 * (int64_t)id + 0] = p[2];  // (axis0, axis1, axis2)
-    verts[3 * (int64_t)id + 1] = p[1];
-    verts[3 * (int64_t)id + 2] = p[0];
-    edge_id[edge_slot(D, zr, y, x, e)] = id;
-    id++;
+    const int64_t id = id0 + v;
+    verts[3 * id + 0] = p[2];  // (axis0, axis1, axis2)
+    verts[3 * id + 1] = p[1];
+    verts[3 * id + 2] = p[0];
+    edge_id[edge_slot(D, cz, cy, cx, e)] = (int)id;
   }
 }
 
@@ -301,28 +343,40 @@ __global__ void top_plane_kernel(const int* __restrict__ edge_id_plane, int* __r
   }
 }
 
-// ---- pass 4: faces, appended cell by cell in table order
-__global__ void __launch_bounds__(CB) emit_faces_kernel(Dims D, const uint16_t* __restrict__ var_in,
-                                                        const int2* __restrict__ block_off, const int* __restrict__ edge_id,
-                                                        int descent, int* __restrict__ faces) {
+// ---- pass 4: faces, appended cell by cell in table order.  One thread per triangle.
+constexpr int MAXT = 12;
+static_assert(MAXT >= DJ_MC_MAXTRI, "triangle list capacity");
+__global__ void __launch_bounds__(CB, 4) emit_faces_kernel(Dims D, const uint16_t* __restrict__ var_in,
+                                                           const int2* __restrict__ block_off,
+                                                           const longlong2* __restrict__ group_off,
+                                                           const int* __restrict__ edge_id, int descent, int* __restrict__ faces) {
   __shared__ int sscan[CB / 32];
-  const int64_t ci = (int64_t)blockIdx.x * CB + threadIdx.x;
+  __shared__ uint16_t slist[CB * MAXT];  // (cell's thread << 4) | triangle index, in face order
+  int zr, y, x;
+  int64_t ci;
   int var = 0, nt = 0;
-  if (ci < D.ncells) {
+  if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
     var = var_in[ci];
     nt = DJ_MC_NTRI[var];
   }
   int tot;
   const int pre = block_excl_scan(nt, sscan, &tot);
-  if (nt == 0) return;
-  int zr, y, x;
-  cell_coords(D, ci, zr, y, x);
-  int64_t fo = (int64_t)block_off[blockIdx.x].y + pre;
-  for (int t = 0; t < nt; t++) {
+  if (tot == 0) return;
+  for (int t = 0; t < nt; t++) slist[pre + t] = (uint16_t)((threadIdx.x << 4) | t);
+  __syncthreads();
+  const int64_t bl = block_linear();
+  const int64_t f0 = (int64_t)block_off[bl].y + group_off[bl >> 10].y;
+  for (int v = threadIdx.x; v < tot; v += CB) {
+    const int ent = slist[v];
+    const int t = ent & 15;
+    int cz, cy, cx;
+    int64_t cci;
+    block_cell(D, ent >> 4, cz, cy, cx, cci);
+    const int cvar = var_in[cci];
     int id[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) id[k] = edge_id[edge_slot(D, zr, y, x, DJ_MC_TRI[var][3 * t + k])];
-    int* o = faces + 3 * (fo + t);
+    for (int k = 0; k < 3; k++) id[k] = edge_id[edge_slot(D, cz, cy, cx, DJ_MC_TRI[cvar][3 * t + k])];
+    int* o = faces + 3 * (f0 + v);
     if (descent) { o[0] = id[2]; o[1] = id[1]; o[2] = id[0]; }
     else { o[0] = id[0]; o[1] = id[1]; o[2] = id[2]; }
   }
