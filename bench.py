@@ -195,8 +195,9 @@ def main():
     dims = (d, d, d)
     npts = d ** 3
     u = args.use_net
-    dec = make_decoder(rank % 2, dev, args.precision)
-    code = synth_data.trained_code(rank)
+    # every rank its own shape: synthetic weights seed r are centred on the shipped latent row r (zero level set exists)
+    dec = make_decoder(rank % 8, dev, args.precision)
+    code = synth_data.trained_code(rank % 8)
     code_dev = code.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
