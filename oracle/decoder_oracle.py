@@ -265,3 +265,30 @@ def select_samples(pts, values, num_samples=None, uniform_ratio=0.5):
             raise NoSamplesError
     idx = np.concatenate([pos_picked, neg_picked])
     return pts[idx, :], values[idx, :]
+
+
+# ---------------------------------------------------------------------------------------------
+# DeepSDF baseline decoder
+# ---------------------------------------------------------------------------------------------
+def deepsdf_forward(sd, latent, pts, dtype=torch.float32, latent_in=4):
+    """Restatement of networks/decoder_deepsdf.py:70-106 for one latent code: x = [z; p]; lin, ReLU (:64,
+    no activation after the last layer :90), input re-injected at ``latent_in`` (:83-84), weight_norm folded
+    (:44-48), final tanh (:103-104).  Returns [N,1]."""
+    sd = {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+    n_layers = 1 + max(int(k[3:].split(".")[0]) for k in sd if k.startswith("lin"))
+    pts = pts.to(dtype)
+    inp = torch.cat([latent.to(dtype).reshape(1, -1).expand(pts.shape[0], -1), pts], 1)
+    x = inp
+    for l in range(n_layers):
+        if "lin%d.weight_v" % l in sd:
+            v = sd["lin%d.weight_v" % l].to(dtype)
+            w = v * (sd["lin%d.weight_g" % l].to(dtype) / v.norm(dim=1, keepdim=True))
+        else:
+            w = sd["lin%d.weight" % l].to(dtype)
+        b = sd["lin%d.bias" % l].to(dtype)
+        if l == latent_in:
+            x = torch.cat([x, inp], 1)
+        x = x @ w.t() + b
+        if l < n_layers - 1:
+            x = torch.relu(x)
+    return torch.tanh(x)

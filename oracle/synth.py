@@ -13,7 +13,8 @@ import numpy as np
 import torch
 
 import synth_data as _S
-from synth_data import GOLDEN, MUGS, layer_shapes, make_code, make_points, make_sample_set, trained_code  # noqa: F401
+from synth_data import (GOLDEN, MUGS, layer_shapes, make_code, make_deepsdf_state_dict, make_points,  # noqa: F401
+                        make_sample_set, trained_code)
 
 
 def compute_head_shifts(sd, a, seed):

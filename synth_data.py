@@ -92,6 +92,19 @@ def _center_sdf_heads(sd, a, seed):
     sd["hnet_lin%d.bias" % (a["h_layers"] - 1)][0] -= shifts[key][1]
 
 
+def make_deepsdf_state_dict(seed=0, kind="default", prefix=""):
+    """State dict of the reference's baseline ``networks.decoder_deepsdf.Decoder`` (mugs_deepsdf specs:
+    latent 128, 8 x 512, latent_in [4], weight_norm): the fnet tensors of make_state_dict with the head cut
+    to its SDF row (keys lin0..lin7 {weight_g, weight_v, bias}, lin8 {weight [1,512], bias [1]})."""
+    sd = make_state_dict(seed, kind)
+    out = {k: v.clone() for k, v in sd.items() if k.startswith("lin")}
+    out["lin8.weight"] = out["lin8.weight"][:1].clone()
+    out["lin8.bias"] = out["lin8.bias"][:1].clone()
+    if prefix:
+        out = {prefix + k: v for k, v in out.items()}
+    return out
+
+
 def trained_code(seed=0):
     """Row `seed` of the reference's shipped LatentCodes/2000.pth || 2000_tool.pth (first 8 rows are
     committed as tests/golden/latent_rows.npz) -- the code the trained-norm weights are centred on."""

@@ -205,3 +205,22 @@ def test_synthetic_weights_do_not_need_the_oracle():
     assert all(torch.equal(a[k], b[k]) for k in a)
     c = synth.make_state_dict(11, "trained_norm")  # no committed shift -> oracle centring
     assert set(c) == set(a)
+
+
+def test_deepsdf_dropin_surface():
+    """the baseline decoder's import names and its rejection of unsupported configurations."""
+    from deepjoin_b200.networks.decoder_deepsdf import Decoder
+    from deepjoin_b200.core import utils_deepsdf
+    ok = dict(dims=[512] * 8, dropout=list(range(8)), dropout_prob=0.2, norm_layers=list(range(8)), latent_in=[4],
+              xyz_in_all=False, use_tanh=False, latent_dropout=False, weight_norm=True)
+    dec = Decoder(128, **ok)
+    import synth_data
+    dec.load_state_dict(synth_data.make_deepsdf_state_dict(0, "default", prefix="module."))
+    assert sorted(k for k in dec.state_dict() if k.startswith("lin8")) == ["lin8.bias", "lin8.weight"]
+    assert tuple(dec.state_dict()["lin8.weight"].shape) == (1, 512)
+    for bad in (dict(use_tanh=True), dict(xyz_in_all=True), dict(latent_in=[2, 4]), dict(dims=[256] * 8), dict(latent_dropout=True)):
+        with pytest.raises(NotImplementedError):
+            Decoder(128, **dict(ok, **bad))
+    assert all(hasattr(utils_deepsdf, n) for n in ("decode_sdf", "create_mesh", "values2mesh"))
+    with pytest.raises(RuntimeError):
+        dec.eval().pack()  # CPU decoder: no fallback

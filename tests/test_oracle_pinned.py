@@ -100,3 +100,14 @@ def test_latent_grad_and_adam_loop(kind):
     assert np.abs(code.numpy() - g[kind + "_code"]).max() < 2e-3
     assert np.abs(np.asarray(log["loss"]) - g[kind + "_log_loss"]).max() < 1e-4
     assert np.allclose(log["mag"], g[kind + "_log_mag"], atol=1e-5)
+
+
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+@pytest.mark.parametrize("seed", [0, 1])
+def test_deepsdf_oracle_matches_reference(kind, seed):
+    """oracle.deepsdf_forward against outputs of the reference's own networks/decoder_deepsdf.py
+    (tests/golden/make_golden_deepsdf.py)."""
+    g = np.load(os.path.join(G, "deepsdf_forward.npz"))
+    sd = synth.make_deepsdf_state_dict(seed, kind)
+    out = O.deepsdf_forward(sd, torch.from_numpy(g["%s_%d_code" % (kind, seed)]), torch.from_numpy(g["%s_%d_pts" % (kind, seed)]))
+    assert np.abs(out.numpy() - g["%s_%d_out" % (kind, seed)]).max() < (5e-6 if kind == "default" else 2e-4)
