@@ -187,3 +187,24 @@ def test_large_grid_properties_256():
     s = R.decode_shape_device(code, dec, dims, use_net=1, padding=0.1, sigmoid=False, rows=(lo, hi))
     assert torch.equal(s, b[lo:hi])
     assert (b.min() < 0) and (b.max() > 0)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 1e-3)])
+def test_latent_size_256_variant(precision, tol):
+    """BASELINE configs[4]: CodeLength = 256 (fnet lin0 [512,259], lin3 [253,512]); every use_net branch
+    against the oracle restatement."""
+    from deepjoin_b200.networks.decoder_z_lb_both_leaky_n_sdf import Decoder
+    arch = dict(latent_size=256, tool_latent_size=64)
+    sd = synth.make_state_dict(2, "default", **arch)
+    dec = Decoder(latent_size=256, tool_latent_size=64, num_dims=3, do_code_regularization=True,
+                  **util.SPECS["NetworkSpecs"], **util.SPECS["SubnetSpecs"])
+    dec.load_state_dict(sd)
+    dec.precision = precision
+    dec = dec.cuda().eval()
+    net = O.fold(sd, **arch)
+    code = synth.make_code(2, 256, 64)
+    pts = synth.make_points(3000, 5)
+    for u in (0, 1, 2, 3):
+        ref = O.forward(net, code, pts, u).numpy()
+        got = dec.query(code.cuda(), pts.cuda(), use_net=u).cpu().numpy()
+        assert np.abs(got - ref).max() <= tol, (u, np.abs(got - ref).max())
