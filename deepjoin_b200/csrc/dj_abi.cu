@@ -12,6 +12,8 @@
 
 using namespace dj;
 
+constexpr int DJ_MAX_BATCH = 64;  // shapes per launch of the batched latent step
+
 // ====================================================================== pack
 struct DjPack {
   DjNetDesc desc{};
@@ -199,7 +201,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
   p->fold.src[0] = {p->fW[0], p->fB[0], L + 3, 0, L, L, 0};
   p->fold.src[1] = {p->fW[li], p->fB[li], H, K3, L, K3 + L, 0};
   p->fold.src[2] = {p->hW[0], p->hB[0], Lb + 3, 0, Lb, Lb, L};
-  DJ_TRY(cudaMalloc((void**)&p->tables, 3 * 512 * sizeof(float4)));
+  DJ_TRY(cudaMalloc((void**)&p->tables, (size_t)DJ_MAX_BATCH * 3 * 512 * sizeof(float4)));  // per-shape constants of up to DJ_MAX_BATCH codes
   DJ_TRY(cudaMalloc((void**)&p->err, sizeof(unsigned int)));
   DJ_TRY(cudaMemset(p->err, 0, sizeof(unsigned int)));
   DJ_TRY(cudaMalloc((void**)&p->prof, (size_t)prop.multiProcessorCount * 16 * sizeof(unsigned long long)));
@@ -730,14 +732,42 @@ static int latent_fwd_bwd(DjPack* p, const float* code_dev, const float* xyz, co
   return DJ_OK;
 }
 
-// tensor-core forward + loss + backward (latent_tc2.cuh); same outputs as latent_fwd_bwd.  idx (optional):
-// the mini-batch's rows of the pool, gathered inside the kernel.
-static int latent_fwd_bwd_tc(DjPack* p, const float* code_dev, const float* xyz, const float* sdf, const float* nrm,
-                             const int32_t* idx, int64_t n, const DjLatentCfg* cfg, LatWs& W, cudaStream_t st) {
-  int rc;
-  if ((rc = launch_fold(p, code_dev, st))) return rc;
-  DJ_CUDA(cudaMemsetAsync(W.colsum, 0, (3 * 512 + 8) * sizeof(float), st));  // colsum + loss_acc are contiguous
-  const int64_t ntiles = (n + lat2::TILE_M - 1) / lat2::TILE_M;
+// Workspace of the tensor-core latent step for a batch of S shapes: accumulators [S][ACC_STRIDE] (column sums +
+// loss terms), grad [S][256], terms [S][8], device pointer table [3][S].
+struct LatTcWs {
+  float *acc, *grad, *terms;
+  const float** ptrs;  // xyz[S] | sdf[S] | nrm[S]
+};
+static int carve_latent_tc(DjPack* p, int S, LatTcWs& W) {
+  const size_t floats = (size_t)S * (lat2::ACC_STRIDE + 256 + 8) + 64;
+  DJ_CUDA(p->ws_lat.reserve(floats * sizeof(float) + (size_t)3 * S * sizeof(void*) + 256));
+  float* q = p->ws_lat.as<float>();
+  W.acc = q; q += (size_t)S * lat2::ACC_STRIDE;
+  W.grad = q; q += (size_t)S * 256;
+  W.terms = q; q += (size_t)S * 8;
+  W.ptrs = reinterpret_cast<const float**>((reinterpret_cast<uintptr_t>(q) + 63) & ~(uintptr_t)63);
+  return DJ_OK;
+}
+// upload the per-shape sample array pointers (once per optimisation, not per iteration)
+static int upload_ptrs(LatTcWs& W, int S, const float* const* xyz, const float* const* sdf, const float* const* nrm, cudaStream_t st) {
+  std::vector<const float*> h((size_t)3 * S);
+  for (int s = 0; s < S; s++) { h[s] = xyz[s]; h[S + s] = sdf[s]; h[2 * S + s] = nrm[s]; }
+  DJ_CUDA(cudaMemcpyAsync(W.ptrs, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+  DJ_CUDA(cudaStreamSynchronize(st));  // h goes out of scope
+  return DJ_OK;
+}
+
+// tensor-core forward + loss + backward (latent_tc2.cuh) for S shapes in ONE launch: codes [S][C] -> grad [S][256],
+// terms [S][8].  idx (optional): this iteration's rows of every shape's pool ([S] rows of n, idx_stride apart),
+// gathered inside the kernel.
+static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int32_t* idx, int64_t idx_stride, int64_t n,
+                             const DjLatentCfg* cfg, LatTcWs& W, cudaStream_t st) {
+  const int C = p->L + p->Lb;
+  simt::fold_kernel<<<dim3((3 * 512 * 32 + 255) / 256, S), 256, 0, st>>>(p->fold, codes_dev, p->tables, C);
+  DJ_LAUNCHED();
+  DJ_CUDA(cudaMemsetAsync(W.acc, 0, (size_t)S * lat2::ACC_STRIDE * sizeof(float), st));
+  const int64_t tps = (n + lat2::TILE_M - 1) / lat2::TILE_M;
+  const int64_t ntiles = tps * S;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);
   const int64_t passes = (ntiles + grid - 1) / grid;
   DJ_CUDA(p->ws_mask.reserve((size_t)passes * grid * lat2::MASK_LAYERS * 8 * 128 * sizeof(unsigned long long)));
@@ -749,12 +779,13 @@ static int latent_fwd_bwd_tc(DjPack* p, const float* code_dev, const float* xyz,
   P.stream[1] = p->lat_stream[1];
   P.bias = p->bias_dev;
   P.tables = p->tables;
-  P.xyz = xyz; P.sdf = sdf; P.nrm = nrm; P.idx = idx;
+  P.xyz = W.ptrs; P.sdf = W.ptrs + S; P.nrm = W.ptrs + 2 * S;
+  P.idx = idx; P.idx_stride = idx_stride;
   P.n = n;
+  P.n_shapes = S; P.tiles_per_shape = (int32_t)tps;
   P.loss = simt::LossCfg{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, p->desc.slope, 1.0f / (float)n};
   P.masks = p->ws_mask.as<unsigned long long>();
-  P.colsum = W.colsum;
-  P.loss_acc = W.loss_acc;
+  P.acc = W.acc;
   P.err = p->err;
   if (!p->lat_attr_set) {
     DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
@@ -763,12 +794,12 @@ static int latent_fwd_bwd_tc(DjPack* p, const float* code_dev, const float* xyz,
   lat2::latent_tc2_kernel<<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
   DJ_LAUNCHED();
   simt::GradFinishParams GP;
-  for (int i = 0; i < 3; i++) { GP.src[i] = p->fold.src[i]; GP.colsum[i] = W.colsum + i * 512; }
+  for (int i = 0; i < 3; i++) { GP.src[i] = p->fold.src[i]; GP.colsum[i] = W.acc + i * 512; }
   GP.L = p->L; GP.Lb = p->Lb;
   GP.reg_lambda = cfg->l2reg ? cfg->code_reg_lambda : 0.f;
-  simt::grad_finish_kernel<<<p->L + p->Lb, 128, 0, st>>>(GP, code_dev, W.grad, W.loss_acc);
+  simt::grad_finish_kernel<<<dim3(C, S), 128, 0, st>>>(GP, codes_dev, W.grad, W.acc + 3 * 512, lat2::ACC_STRIDE, C, 256);
   DJ_LAUNCHED();
-  simt::loss_finish_kernel<<<1, 32, 0, st>>>(W.loss_acc, W.terms);
+  simt::loss_finish_kernel<<<S, 32, 0, st>>>(W.acc + 3 * 512, W.terms, lat2::ACC_STRIDE, 8);
   DJ_LAUNCHED();
   return DJ_OK;
 }
@@ -788,14 +819,73 @@ extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz
   if ((rc = check_latent_cfg(p, cfg))) return rc;
   DeviceGuard g(p->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (cfg->precision == DJ_PREC_BF16) {
+    LatTcWs T;
+    if ((rc = carve_latent_tc(p, 1, T))) return rc;
+    if ((rc = upload_ptrs(T, 1, &xyz_dev, &sdf_dev, &nrm_dev, st))) return rc;
+    if ((rc = latent_fwd_bwd_tc(p, 1, code_dev, nullptr, 0, n, cfg, T, st))) return rc;
+    if ((rc = check_err_word(p, st))) return rc;
+    DJ_CUDA(cudaMemcpyAsync(grad_dev, T.grad, (p->L + p->Lb) * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    if (loss_terms_dev) DJ_CUDA(cudaMemcpyAsync(loss_terms_dev, T.terms, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return DJ_OK;
+  }
   LatWs W;
-  if ((rc = carve_latent(p, n, W, cfg->precision == DJ_PREC_BF16))) return rc;
-  if (cfg->precision == DJ_PREC_BF16) rc = latent_fwd_bwd_tc(p, code_dev, xyz_dev, sdf_dev, nrm_dev, nullptr, n, cfg, W, st);
-  else rc = latent_fwd_bwd(p, code_dev, xyz_dev, sdf_dev, nrm_dev, n, cfg, W, st);
-  if (rc) return rc;
-  if (cfg->precision == DJ_PREC_BF16 && (rc = check_err_word(p, st))) return rc;
+  if ((rc = carve_latent(p, n, W))) return rc;
+  if ((rc = latent_fwd_bwd(p, code_dev, xyz_dev, sdf_dev, nrm_dev, n, cfg, W, st))) return rc;
   DJ_CUDA(cudaMemcpyAsync(grad_dev, W.grad, (p->L + p->Lb) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (loss_terms_dev) DJ_CUDA(cudaMemcpyAsync(loss_terms_dev, W.terms, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  return DJ_OK;
+}
+
+extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_dev, float* adam_m_dev, float* adam_v_dev,
+                                        const float* const* pool_xyz_dev, const float* const* pool_sdf_dev,
+                                        const float* const* pool_nrm_dev, const int64_t* pool_n, const int32_t* idx_dev,
+                                        const DjLatentCfg* cfg, float* log_dev, void* stream) {
+  if (!p || !codes_dev || !adam_m_dev || !adam_v_dev || !pool_xyz_dev || !pool_sdf_dev || !pool_nrm_dev || !pool_n || !idx_dev)
+    return fail(DJ_ERR_INVALID, "dj_latent_optimize_batch: null argument");
+  if (n_shapes < 1 || n_shapes > DJ_MAX_BATCH) return fail(DJ_ERR_INVALID, "dj_latent_optimize_batch: 1..%d shapes per call (got %d)", DJ_MAX_BATCH, n_shapes);
+  for (int s = 0; s < n_shapes; s++)
+    if (!pool_xyz_dev[s] || !pool_sdf_dev[s] || !pool_nrm_dev[s] || pool_n[s] <= 0) return fail(DJ_ERR_INVALID, "dj_latent_optimize_batch: bad pool %d", s);
+  int rc;
+  if ((rc = check_latent_cfg(p, cfg))) return rc;
+  if (cfg->num_iterations < 1 || cfg->num_samples < 1) return fail(DJ_ERR_INVALID, "dj_latent_optimize: iterations/samples must be >= 1");
+  DeviceGuard g(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t n = cfg->num_samples;
+  const int C = p->L + p->Lb;
+  const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
+  const int64_t log_rows = (cfg->num_iterations + log_every - 1) / log_every;
+  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations};
+  if (cfg->precision == DJ_PREC_BF16) {
+    // all shapes in one launch per iteration; the kernel gathers every shape's mini-batch rows itself
+    LatTcWs T;
+    if ((rc = carve_latent_tc(p, n_shapes, T))) return rc;
+    if ((rc = upload_ptrs(T, n_shapes, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, st))) return rc;
+    const int64_t idx_stride = (int64_t)cfg->num_iterations * n;
+    for (int e = 0; e < cfg->num_iterations; e++) {
+      if ((rc = latent_fwd_bwd_tc(p, n_shapes, codes_dev, idx_dev + (size_t)e * n, idx_stride, n, cfg, T, st))) return rc;
+      float* row = (log_dev && e % log_every == 0) ? log_dev + (size_t)(e / log_every) * 8 : nullptr;
+      simt::adam_kernel<<<n_shapes, 256, 0, st>>>(A, e, codes_dev, adam_m_dev, adam_v_dev, T.grad, C, T.terms, row, p->L, C, 256, 8,
+                                                  (long long)log_rows * 8);
+      DJ_LAUNCHED();
+    }
+    return DJ_OK;
+  }
+  // fp32 (reference arithmetic): shape after shape
+  LatWs W;
+  if ((rc = carve_latent(p, n, W))) return rc;
+  for (int s = 0; s < n_shapes; s++) {
+    float* code = codes_dev + (size_t)s * C;
+    const int32_t* idx = idx_dev + (size_t)s * cfg->num_iterations * n;
+    for (int e = 0; e < cfg->num_iterations; e++) {
+      simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev[s], pool_sdf_dev[s], pool_nrm_dev[s], idx + (size_t)e * n, (int)n, W.bx, W.bs, W.bn);
+      DJ_LAUNCHED();
+      if ((rc = latent_fwd_bwd(p, code, W.bx, W.bs, W.bn, n, cfg, W, st))) return rc;
+      float* row = (log_dev && e % log_every == 0) ? log_dev + ((size_t)s * log_rows + e / log_every) * 8 : nullptr;
+      simt::adam_kernel<<<1, 256, 0, st>>>(A, e, code, adam_m_dev + (size_t)s * C, adam_v_dev + (size_t)s * C, W.grad, C, W.terms, row, p->L);
+      DJ_LAUNCHED();
+    }
+  }
   return DJ_OK;
 }
 
@@ -803,32 +893,8 @@ extern "C" int dj_latent_optimize(DjPack* p, float* code_dev, float* adam_m_dev,
                                   const float* pool_xyz_dev, const float* pool_sdf_dev, const float* pool_nrm_dev,
                                   int64_t pool_n, const int32_t* idx_dev, const DjLatentCfg* cfg, float* log_dev,
                                   void* stream) {
-  if (!p || !code_dev || !adam_m_dev || !adam_v_dev || !pool_xyz_dev || !pool_sdf_dev || !pool_nrm_dev || !idx_dev || pool_n <= 0)
-    return fail(DJ_ERR_INVALID, "dj_latent_optimize: bad argument");
-  int rc;
-  if ((rc = check_latent_cfg(p, cfg))) return rc;
-  if (cfg->num_iterations < 1 || cfg->num_samples < 1) return fail(DJ_ERR_INVALID, "dj_latent_optimize: iterations/samples must be >= 1");
-  DeviceGuard g(p->device);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int64_t n = cfg->num_samples;
-  LatWs W;
-  if ((rc = carve_latent(p, n, W, cfg->precision == DJ_PREC_BF16))) return rc;
-  const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
-  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations};
-  for (int e = 0; e < cfg->num_iterations; e++) {
-    if (cfg->precision == DJ_PREC_BF16) {
-      // the kernel gathers the mini-batch rows itself
-      if ((rc = latent_fwd_bwd_tc(p, code_dev, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, idx_dev + (size_t)e * n, n, cfg, W, st))) return rc;
-    } else {
-      simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, idx_dev + (size_t)e * n, (int)n, W.bx, W.bs, W.bn);
-      DJ_LAUNCHED();
-      if ((rc = latent_fwd_bwd(p, code_dev, W.bx, W.bs, W.bn, n, cfg, W, st))) return rc;
-    }
-    float* row = (log_dev && e % log_every == 0) ? log_dev + (size_t)(e / log_every) * 8 : nullptr;
-    simt::adam_kernel<<<1, 256, 0, st>>>(A, e, code_dev, adam_m_dev, adam_v_dev, W.grad, p->L + p->Lb, W.terms, row, p->L);
-    DJ_LAUNCHED();
-  }
-  return DJ_OK;
+  return dj_latent_optimize_batch(p, 1, code_dev, adam_m_dev, adam_v_dev, &pool_xyz_dev, &pool_sdf_dev, &pool_nrm_dev, &pool_n,
+                                  idx_dev, cfg, log_dev, stream);
 }
 
 extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int num_iterations, int num_samples,

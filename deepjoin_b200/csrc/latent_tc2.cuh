@@ -52,6 +52,7 @@ using tc2::TM_ACC;
 
 constexpr int MAX_PROG = 32;
 constexpr int MASK_LAYERS = 13;  // hidden activations whose sign the backward needs (8 fnet + 5 hnet)
+constexpr int ACC_STRIDE = 3 * 512 + 8;  // per shape: colsum[3][512] | loss terms [8]
 
 enum {
   K_L0 = 0,        // epilogue only: layer 0 on CUDA cores -> shared-memory activations
@@ -77,15 +78,19 @@ struct Params {
   const uint8_t* stream[2];  // per cluster rank, stages in program order
   const float* bias;
   const float4* tables;      // [3][512] per-shape constants (fold_kernel)
-  const float* xyz;          // sample pool or batch [.,3]
-  const float* sdf;          // [.]
-  const float* nrm;          // [.,3]
+  // Several shapes (latent codes) share one launch: tile t belongs to shape t / tiles_per_shape.  Per shape s:
+  // tables + s*3*512, sample arrays xyz[s] / sdf[s] / nrm[s], index row idx + s*idx_stride, accumulators
+  // acc + s*ACC_STRIDE ([3][512] column sums then [8] loss terms).
+  const float* const* xyz;   // device array [n_shapes] of sample pools / batches [.,3]
+  const float* const* sdf;   // [.]
+  const float* const* nrm;   // [.,3]
   const int32_t* idx;        // nullptr: rows 0..n-1; else the mini-batch's row indices into the pool
-  int64_t n;
+  int64_t idx_stride;
+  int64_t n;                 // samples per shape
+  int32_t n_shapes, tiles_per_shape;
   simt::LossCfg loss;
   unsigned long long* masks;  // [tiles][MASK_LAYERS][4][2][128]
-  float* colsum;              // [3][512], zeroed by the caller
-  float* loss_acc;            // [8],     zeroed by the caller
+  float* acc;                 // [n_shapes][ACC_STRIDE], zeroed by the caller
   unsigned int* err;
 };
 
@@ -121,7 +126,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+  const int64_t ntiles = (int64_t)P.n_shapes * P.tiles_per_shape;
   const int64_t iters = (ntiles + gridDim.x - 1) / gridDim.x;
 
   if (warp == 0 && lane == 0) {
@@ -297,15 +302,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
 
     for (int64_t it = 0; it < iters; it++) {
       const int64_t tile = it * gridDim.x + blockIdx.x;
-      const int64_t g = tile * TILE_M + row;
-      const bool live = g < P.n;
+      const int shape_raw = (int)(tile / P.tiles_per_shape);
+      const int shape = shape_raw < P.n_shapes ? shape_raw : 0;  // passes beyond the last tile: dead rows of shape 0
+      const int64_t g = (tile - (int64_t)shape_raw * P.tiles_per_shape) * TILE_M + row;  // sample within the shape
+      const bool live = shape_raw < P.n_shapes && g < P.n;
+      const float4* tables = P.tables + (size_t)shape * 3 * 512;
+      float* colsum = P.acc + (size_t)shape * ACC_STRIDE;
+      float* loss_acc = colsum + 3 * 512;
       float x = 0.f, y = 0.f, z = 0.f, s_gt = 0.f, n_gt[3] = {0.f, 0.f, 0.f};
       if (live) {
-        const int64_t r = P.idx ? (int64_t)__ldg(P.idx + g) : g;
-        x = __ldg(P.xyz + 3 * r); y = __ldg(P.xyz + 3 * r + 1); z = __ldg(P.xyz + 3 * r + 2);
+        const int64_t r = P.idx ? (int64_t)__ldg(P.idx + (size_t)shape * P.idx_stride + g) : g;
+        const float* px = P.xyz[shape];
+        x = __ldg(px + 3 * r); y = __ldg(px + 3 * r + 1); z = __ldg(px + 3 * r + 2);
         if (h == 0) {
-          s_gt = __ldg(P.sdf + r);
-          n_gt[0] = __ldg(P.nrm + 3 * r); n_gt[1] = __ldg(P.nrm + 3 * r + 1); n_gt[2] = __ldg(P.nrm + 3 * r + 2);
+          const float* pn = P.nrm[shape];
+          s_gt = __ldg(P.sdf[shape] + r);
+          n_gt[0] = __ldg(pn + 3 * r); n_gt[1] = __ldg(pn + 3 * r + 1); n_gt[2] = __ldg(pn + 3 * r + 2);
         }
       }
       unsigned long long* mrow = P.masks + ((size_t)tile * MASK_LAYERS * 8 + (size_t)h) * 128 + row;  // + (layer*4 + chunk)*256
@@ -318,7 +330,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
           // ---- layer 0 on CUDA cores (K = 3 after folding the latent into table.w) -> shared-memory activations
           tc::epi_bar();
           {
-            const float4* t = P.tables + L.slot * 512;
+            const float4* t = tables + L.slot * 512;
             sTab[et] = __ldg(t + et);
             sTab[et + 256] = __ldg(t + et + 256);
           }
@@ -379,7 +391,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
                 l3[1] += __shfl_xor_sync(0xffffffffu, l3[1], o);
                 l3[2] += __shfl_xor_sync(0xffffffffu, l3[2], o);
               }
-              if (lane < 3) atomicAdd(P.loss_acc + lane, lane == 0 ? l3[0] : (lane == 1 ? l3[1] : l3[2]));
+              if (lane < 3) atomicAdd(loss_acc + lane, lane == 0 ? l3[0] : (lane == 1 ? l3[1] : l3[2]));
             }
             // the hnet head read the shared-memory activations; its MMAs are complete (accumulator barrier above)
             write_head_operand(gt);
@@ -393,7 +405,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
           if (L.kind == K_FWD) {
             reinterpret_cast<float2*>(sBias)[et] = __ldg(reinterpret_cast<const float2*>(P.bias + L.bias_off) + et);
           } else {
-            const float4* t = P.tables + L.slot * 512;
+            const float4* t = tables + L.slot * 512;
             sTab[et] = __ldg(t + et);
             sTab[et + 256] = __ldg(t + et + 256);
           }
@@ -482,7 +494,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
 #pragma unroll
             for (int i = 0; i < 32; i++) { lo[i] = vf[i]; hi[i] = vf[32 + i]; }
             const float s0 = warp_colsum32(lo, lane), s1 = warp_colsum32(hi, lane);
-            float* cs = P.colsum + L.slot * 512 + col0;
+            float* cs = colsum + L.slot * 512 + col0;
             atomicAdd(cs + lane, s0);
             atomicAdd(cs + 32 + lane, s1);
           }

@@ -27,7 +27,10 @@ struct FoldParams {
   FoldSrc src[3];
 };
 
-__global__ void fold_kernel(FoldParams P, const float* __restrict__ code, float4* __restrict__ tables) {
+// blockIdx.y = shape of a batch: code + y*code_stride -> tables + y*3*512 (strides 0 / grid.y 1 for one shape)
+__global__ void fold_kernel(FoldParams P, const float* __restrict__ code, float4* __restrict__ tables, int code_stride = 0) {
+  code += (size_t)blockIdx.y * code_stride;
+  tables += (size_t)blockIdx.y * 3 * 512;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (w >= 3 * 512) return;
@@ -299,17 +302,23 @@ struct GradFinishParams {
   int L, Lb;
   float reg_lambda;        // 0 when !l2reg
 };
+// blockIdx.y = shape of a batch: accumulators (colsum, loss_acc) + y*acc_stride, code + y*code_stride,
+// grad + y*grad_stride (all strides 0 with grid.y 1 for one shape)
 __global__ void grad_finish_kernel(GradFinishParams P, const float* __restrict__ code, float* __restrict__ grad,
-                                   float* __restrict__ loss_acc) {
+                                   float* __restrict__ loss_acc, int acc_stride = 0, int code_stride = 0, int grad_stride = 0) {
   const int i = blockIdx.x;  // code element
   const int tot = P.L + P.Lb;
   if (i >= tot) return;
+  code += (size_t)blockIdx.y * code_stride;
+  grad += (size_t)blockIdx.y * grad_stride;
+  loss_acc += (size_t)blockIdx.y * acc_stride;
   float acc = 0.f;
   for (int t = 0; t < 3; t++) {
     const FoldSrc S = P.src[t];
     const int li = i - S.code_off;
     if (li < 0 || li >= S.lat_n) continue;
-    for (int j = threadIdx.x; j < 512; j += blockDim.x) acc = fmaf(P.colsum[t][j], S.W[(size_t)j * S.ld + S.lat_off + li], acc);
+    const float* cs = P.colsum[t] + (size_t)blockIdx.y * acc_stride;
+    for (int j = threadIdx.x; j < 512; j += blockDim.x) acc = fmaf(cs[j], S.W[(size_t)j * S.ld + S.lat_off + li], acc);
   }
   __shared__ float red[32];
 #pragma unroll
@@ -328,7 +337,10 @@ __global__ void grad_finish_kernel(GradFinishParams P, const float* __restrict__
 }
 
 // loss_terms[5] = (total, sdf, occ, norm, reg) from the accumulators
-__global__ void loss_finish_kernel(const float* __restrict__ loss_acc, float* __restrict__ terms) {
+__global__ void loss_finish_kernel(const float* __restrict__ loss_acc, float* __restrict__ terms, int acc_stride = 0,
+                                   int terms_stride = 0) {
+  loss_acc += (size_t)blockIdx.x * acc_stride;  // blockIdx.x = shape of a batch
+  terms += (size_t)blockIdx.x * terms_stride;
   if (threadIdx.x == 0) {
     const float s = loss_acc[0], o = loss_acc[1], nn = loss_acc[2], r = loss_acc[3];
     terms[0] = s + o + nn + r;
@@ -341,9 +353,18 @@ struct AdamCfg {
   float lr, beta1, beta2, eps;
   int num_iterations;
 };
+// blockIdx.x = shape of a batch (code / m / v + x*code_stride, grad + x*grad_stride, terms + x*terms_stride,
+// log_row + x*log_stride)
 __global__ void adam_kernel(AdamCfg A, int e, float* __restrict__ code, float* __restrict__ m, float* __restrict__ v,
                             const float* __restrict__ grad, int n, const float* __restrict__ terms,
-                            float* __restrict__ log_row, int L) {
+                            float* __restrict__ log_row, int L, int code_stride = 0, int grad_stride = 0, int terms_stride = 0,
+                            long long log_stride = 0) {
+  code += (size_t)blockIdx.x * code_stride;
+  m += (size_t)blockIdx.x * code_stride;
+  v += (size_t)blockIdx.x * code_stride;
+  grad += (size_t)blockIdx.x * grad_stride;
+  terms += (size_t)blockIdx.x * terms_stride;
+  if (log_row) log_row += (size_t)blockIdx.x * log_stride;
   const int i = threadIdx.x;
   __shared__ float sq[2];
   if (i < 2) sq[i] = 0.f;

@@ -67,6 +67,40 @@ def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, la
     return log, code.reshape(1, -1)
 
 
+def optimize_codes(decoder, codes0, pools, schedules, lr, lambda1, lambda3, clamp_dist, l2reg=True, code_reg_lambda=1e-4,
+                   log_every=10, precision="bf16"):
+    """The device loop for S independent shapes at once (extension; the reference's worker runs them one after
+    the other, core/utils_multiprocessing.py:33-71).  codes0 [S, L+Lb]; pools: S tuples (xyz [M,3], sdf [M],
+    nrm [M,3]) of CUDA f32 tensors; schedules CUDA int32 [S, iterations, num_samples].
+    Returns (logs [S, ceil(it/log_every), 8] CUDA, codes [S, L+Lb] CUDA).  With precision "bf16" every
+    iteration is one fused tensor-core launch over all shapes (dj_latent_optimize_batch)."""
+    import ctypes
+    S = int(schedules.shape[0])
+    if len(pools) != S or int(codes0.shape[0]) != S:
+        raise ValueError("need one pool and one code per schedule")
+    dev = schedules.device
+    pack = decoder.pack(dev)
+    iters, ns = int(schedules.shape[1]), int(schedules.shape[2])
+    cfg = _lib.LatentCfg(iters, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
+                         float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, int(log_every),
+                         _lib.PREC[precision])
+    codes = codes0.detach().to(device=dev, dtype=torch.float32).reshape(S, -1).clone().contiguous()
+    m = torch.zeros_like(codes)
+    v = torch.zeros_like(codes)
+    logs = torch.zeros((S, (iters + log_every - 1) // log_every, 8), device=dev, dtype=torch.float32)
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    keep = [(f32(x), f32(s).reshape(-1), f32(n)) for x, s, n in pools]
+    arr = lambda k: (ctypes.c_void_p * S)(*[t[k].data_ptr() for t in keep])
+    pn = (ctypes.c_int64 * S)(*[int(t[0].shape[0]) for t in keep])
+    sched = schedules.to(torch.int32).contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().dj_latent_optimize_batch(
+            pack.handle, S, codes.data_ptr(), m.data_ptr(), v.data_ptr(), arr(0), arr(1), arr(2), pn, sched.data_ptr(),
+            ctypes.byref(cfg), logs.data_ptr(), _lib.stream_ptr()))
+        torch.cuda.current_stream().synchronize()  # `keep` / the pointer arrays must outlive the enqueued loop
+    return logs, codes
+
+
 def latent_grad(decoder, code, xyz, sdf, nrm, lambda1=1.0, lambda3=1.0, clamp_dist=0.1, l2reg=True,
                 code_reg_lambda=1e-4, precision="fp32"):
     """One forward+backward: (dL/dcode [L+Lb], loss terms [5] = loss, sdf, occ, norm, reg)."""

@@ -135,6 +135,16 @@ int dj_latent_optimize(DjPack* pack, float* code_dev, float* adam_m_dev, float* 
                        int64_t pool_n, const int32_t* idx_dev, const DjLatentCfg* cfg,
                        float* log_dev, void* stream);
 
+/* The same loop for n_shapes (<= 64) independent shapes at once (what a reconstruct_chunk worker does item
+ * after item, core/utils_multiprocessing.py:33-71): with DJ_PREC_BF16 every iteration is ONE launch over all
+ * shapes' mini-batches, which fills the tile slots a single 30,000-sample batch leaves idle.
+ * codes / adam_m / adam_v [n_shapes, L+Lb]; pool_*_dev, pool_n: HOST arrays of n_shapes device pointers / row
+ * counts; idx_dev [n_shapes, iterations, num_samples]; log_dev [n_shapes, ceil(iters/log_every), 8]. */
+int dj_latent_optimize_batch(DjPack* pack, int n_shapes, float* codes_dev, float* adam_m_dev, float* adam_v_dev,
+                             const float* const* pool_xyz_dev, const float* const* pool_sdf_dev,
+                             const float* const* pool_nrm_dev, const int64_t* pool_n, const int32_t* idx_dev,
+                             const DjLatentCfg* cfg, float* log_dev, void* stream);
+
 /* replaces: core.data.select_samples(pts, values, num_samples, uniform_ratio)
  * (core/data.py:15-73,122-176) for every iteration at once, on the device, from a counter
  * based RNG (same distribution, not numpy's stream): keep the surface half, a random

@@ -211,3 +211,32 @@ def test_reconstruct_follows_decoder_precision():
                              l2reg=True, sampling_method="device")
     assert loss["epoch"] == [0, 10, 20, 30] and loss["loss"][-1] < loss["loss"][0]
     assert torch.isfinite(code).all()
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+def test_batched_shapes_equal_one_by_one(precision):
+    """dj_latent_optimize_batch: S shapes in one launch per iteration == the same shapes optimised separately
+    (bf16: up to the order of the atomic column sums)."""
+    from deepjoin_b200 import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision=precision)
+    S, iters, ns = 3, 12 if precision == "bf16" else 4, 1000
+    pools, scheds, codes0 = [], [], []
+    for s in range(S):
+        xyz, sdf, nrm = synth.make_sample_set(6000 + 500 * s, seed=10 + s)
+        pools.append(tuple(torch.from_numpy(a.astype(np.float32)).cuda() for a in (xyz, sdf.reshape(-1), nrm)))
+        scheds.append(torch.from_numpy(np.random.default_rng(s).integers(0, 6000, (iters, ns)).astype(np.int32)))
+        torch.manual_seed(s)
+        codes0.append(R.init_code(128, 64, 0.01))
+    sched = torch.stack(scheds).cuda()
+    logs, codes = R.optimize_codes(dec, torch.cat(codes0), pools, sched, 5e-3, 1.0, 1.0, 0.1, l2reg=True, precision=precision)
+    assert tuple(logs.shape) == (S, 2 if precision == "bf16" else 1, 8) and tuple(codes.shape) == (S, 192)
+    for s in range(S):
+        log1, code1 = R.optimize_code(dec, codes0[s], *pools[s], sched[s], 5e-3, 1.0, 1.0, 0.1, l2reg=True, precision=precision)
+        a, b = logs[s].cpu().numpy(), log1.cpu().numpy()
+        assert np.allclose(a[0], b[0], rtol=1e-4, atol=1e-6), s  # iteration 0: same arithmetic
+        # later iterations: the atomic column sums add in a different order, Adam (step = lr per element whatever
+        # the gradient's size) amplifies that to a few lr
+        tol = 3e-2 if precision == "bf16" else 2e-3
+        assert np.allclose(a, b, rtol=tol, atol=tol), s
+        assert np.abs(codes[s].cpu().numpy() - code1.cpu().numpy().reshape(-1)).max() < (2e-2 if precision == "bf16" else 2e-3), s
+    assert not np.allclose(codes[0].cpu().numpy(), codes[1].cpu().numpy(), atol=1e-3)  # really different shapes
