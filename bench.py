@@ -260,48 +260,60 @@ def main():
     if args.latent_shapes and not args.query_only:
         from deepjoin_b200 import reconstruct as RR
         n_sh, iters_l, ns_l = args.latent_shapes, 800, 30000
-        xyz_s, sdf_s, nrm_s = synth_data.make_sample_set(100000, seed=rank)
-        px = torch.from_numpy(xyz_s.astype(np.float32)).to(dev)
-        ps = torch.from_numpy(sdf_s.astype(np.float32).reshape(-1)).to(dev)
-        pn = torch.from_numpy(nrm_s.astype(np.float32)).to(dev)
-        sched = torch.empty((iters_l, ns_l), device=dev, dtype=torch.int32)
+        pools = []
+        for sh in range(n_sh):  # every shape its own synthetic fractured-mug sample set (resident in HBM)
+            xyz_s, sdf_s, nrm_s = synth_data.make_sample_set(100000, seed=rank * n_sh + sh)
+            pools.append((torch.from_numpy(xyz_s.astype(np.float32)).to(dev), torch.from_numpy(sdf_s.astype(np.float32).reshape(-1)).to(dev),
+                          torch.from_numpy(nrm_s.astype(np.float32)).to(dev)))
+        sched = torch.empty((n_sh, iters_l, ns_l), device=dev, dtype=torch.int32)
 
-        def one_shape(seed, n_it):
-            _lib.check(_lib.lib().dj_sample_schedule(ps.data_ptr(), ps.shape[0], n_it, ns_l, 0.2, 1000 + seed, sched.data_ptr(),
-                                                     _lib.stream_ptr()))
-            torch.manual_seed(seed)
-            log, c = RR.optimize_code(dec, RR.init_code(128, 64, 0.01), px, ps, pn, sched[:n_it], 5e-3, 1.0, 1.0, 0.1,
-                                      l2reg=True, code_reg_lambda=1e-4, precision=args.precision)
-            m = R.create_mesh(c, dec, 2, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
-            return log, m
+        def run_shapes(n_it):
+            """configs[2] on this rank: draw every shape's mini-batch schedule on the device, optimise all codes with
+            one fused launch per Adam iteration, then extract each shape's restoration mesh."""
+            for sh in range(n_sh):
+                _lib.check(_lib.lib().dj_sample_schedule(pools[sh][1].data_ptr(), pools[sh][1].shape[0], n_it, ns_l, 0.2,
+                                                         1000 + rank * n_sh + sh, sched[sh].data_ptr(), _lib.stream_ptr()))
+            codes0 = []
+            for sh in range(n_sh):
+                torch.manual_seed(rank * n_sh + sh)
+                codes0.append(RR.init_code(128, 64, 0.01))
+            t_a = torch.cuda.Event(enable_timing=True)
+            t_b = torch.cuda.Event(enable_timing=True)
+            t_a.record()
+            logs, codes = RR.optimize_codes(dec, torch.cat(codes0), pools, sched[:, :n_it], 5e-3, 1.0, 1.0, 0.1, l2reg=True,
+                                            code_reg_lambda=1e-4, precision=args.precision)
+            t_b.record()
+            torch.cuda.synchronize()
+            run_shapes.opt_ms = t_a.elapsed_time(t_b)
+            n_ok = 0
+            for sh in range(n_sh):
+                try:
+                    R.create_mesh(codes[sh], dec, 2, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
+                    n_ok += 1
+                except Exception:  # IsosurfaceExtractionError -> empty mesh, as the reference's mesh_chunk does
+                    pass
+            return logs, n_ok
 
-        try:
-            one_shape(0, 20)
-        except Exception:  # restoration surface may be empty for a barely optimised code: warm-up only
-            pass
+        run_shapes(10)
         barrier()
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         wl = time.perf_counter()
         l0.record()
-        n_mesh, last_loss = 0, None
-        for sh in range(n_sh):
-            try:
-                log, m = one_shape(rank * n_sh + sh, iters_l)
-                n_mesh += 1
-                last_loss = float(log[-1, 1])
-            except Exception as e:  # IsosurfaceExtractionError -> empty mesh, as the reference's mesh_chunk does
-                last_loss = None
+        logs, n_mesh = run_shapes(iters_l)
         l1.record()
         torch.cuda.synchronize()
         tl = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tl, op=dist.ReduceOp.MAX)
         if rank == 0:
-            latent = {"workload": "configs[2]: %d shapes per GPU x %d Adam iterations x %d samples (device sampler, fused "
-                                  "forward+backward tensor-core step), then one %d^3 restoration mesh per shape" % (n_sh, iters_l, ns_l, d),
+            latent = {"workload": "configs[2]: %d shapes per GPU x %d Adam iterations x %d samples (device sampler, all shapes of a "
+                                  "rank in one fused forward+backward tensor-core launch per iteration), then one %d^3 restoration "
+                                  "mesh per shape" % (n_sh, iters_l, ns_l, d),
                       "shapes_per_s": world * n_sh / (float(tl[0]) * 1e-3), "ms_per_shape": float(tl[0]) / n_sh,
                       "wall_ms_per_shape": 1e3 * (time.perf_counter() - wl) / n_sh, "meshes_with_surface": n_mesh,
-                      "final_loss_last_shape": last_loss, "precision": args.precision}
+                      "adam_loop_ms_per_shape": run_shapes.opt_ms / n_sh,
+                      "adam_loop_tflops_alg": n_sh * iters_l * ns_l * 11.03e6 / (run_shapes.opt_ms * 1e-3) / 1e12,
+                      "loss_first_last_shape0": [float(logs[0, 0, 1]), float(logs[0, -1, 1])], "precision": args.precision}
     slab = None
     if args.slab_dims:
         from deepjoin_b200 import parallel as Par
