@@ -467,11 +467,12 @@ static int fp32_forward(DjPack* p, const float* xyz, int64_t n, int net_mask, fl
   return DJ_OK;
 }
 
+// do_fold = false: the caller already folded this code into the pack's tables (several launches with one code)
 static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, const GridSpec& G, int64_t n,
-                       const HeadCfg& head, int net_mask, int precision, float* out_dev, cudaStream_t st) {
+                       const HeadCfg& head, int net_mask, int precision, float* out_dev, cudaStream_t st, bool do_fold = true) {
   if (n <= 0) return DJ_OK;
   int rc;
-  if ((rc = launch_fold(p, code_dev, st))) return rc;
+  if (do_fold && (rc = launch_fold(p, code_dev, st))) return rc;
   if (precision == DJ_PREC_BF16 && p->tc_kernel == 2) {
     tc2::Params P;
     memset(&P, 0, sizeof P);
@@ -620,31 +621,56 @@ extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const d
   if (!p || !code_host || (!pts_host && n > 0) || (!out_host && n > 0) || n < 0) return fail(DJ_ERR_INVALID, "dj_decode_samples_host: bad argument");
   if (use_net < 0 || use_net > 3) return fail(DJ_ERR_BAD_NET, "Requested output from non-existent network: %d", use_net);
   DeviceGuard g(p->device);
-  const int64_t CH = 1 << 22;
+  // chunks of 2^21 points ping-pong over two streams / two workspace halves, so that chunk k+1's upload (f64
+  // points, PCIe) overlaps chunk k's decoder kernel and download
+  const int64_t CH = 1 << 21;
   const int64_t c = std::min<int64_t>(CH, std::max<int64_t>(n, 1));
   const int nc = p->L + p->Lb;
-  // [code | pts f64 | pts f32 | out f32 | out f64]
-  const size_t o_code = 0, o_p64 = 1024, o_p32 = o_p64 + (size_t)c * 24, o_o32 = o_p32 + (size_t)c * 12,
-               o_o64 = (o_o32 + (size_t)c * 4 + 15) & ~(size_t)15;
-  DJ_CUDA(p->ws_host.reserve(o_o64 + (size_t)c * 8));
-  uint8_t* w = p->ws_host.as<uint8_t>();
-  cudaStream_t st = 0;
-  DJ_CUDA(cudaMemcpyAsync(w + o_code, code_host, nc * sizeof(float), cudaMemcpyHostToDevice, st));
+  // [code | 2 x (pts f64 | pts f32 | out f32 | out f64)]
+  const size_t o_p64 = 0, o_p32 = o_p64 + (size_t)c * 24, o_o32 = o_p32 + (size_t)c * 12,
+               o_o64 = (o_o32 + (size_t)c * 4 + 15) & ~(size_t)15, half = (o_o64 + (size_t)c * 8 + 255) & ~(size_t)255;
+  DJ_CUDA(p->ws_host.reserve(1024 + 2 * half));
+  uint8_t* w0 = p->ws_host.as<uint8_t>();
+  cudaStream_t sts[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; i++) DJ_CUDA(cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking));
+  auto cleanup = [&](int rc) {
+    for (int i = 0; i < 2; i++) {
+      cudaStreamSynchronize(sts[i]);
+      cudaStreamDestroy(sts[i]);
+    }
+    return rc;
+  };
+  if (cudaMemcpyAsync(w0, code_host, nc * sizeof(float), cudaMemcpyHostToDevice, sts[0]) != cudaSuccess ||
+      cudaStreamSynchronize(sts[0]) != cudaSuccess)
+    return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: code upload failed"));
+  {  // the fold writes the pack's shared tables: once, before either stream launches a decoder kernel
+    int rc = launch_fold(p, (const float*)w0, sts[0]);
+    if (rc) return cleanup(rc);
+    if (cudaStreamSynchronize(sts[0]) != cudaSuccess) return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: fold failed"));
+  }
   HeadCfg H{OUT_SINGLE, use_net, return_occ, apply_sigmoid, p->desc.slope};
-  for (int64_t s = 0; s < n; s += CH) {
+  int k = 0;
+  for (int64_t s = 0; s < n; s += CH, k++) {
     const int64_t m = std::min(CH, n - s);
-    DJ_CUDA(cudaMemcpyAsync(w + o_p64, pts_host + 3 * s, (size_t)m * 24, cudaMemcpyHostToDevice, st));
+    // the fp32 path works in one shared activation workspace: it stays on one stream
+    const int lane = (precision == DJ_PREC_BF16) ? (k & 1) : 0;
+    cudaStream_t st = sts[lane];
+    uint8_t* w = w0 + 1024 + (size_t)lane * half;
+    if (cudaMemcpyAsync(w + o_p64, pts_host + 3 * s, (size_t)m * 24, cudaMemcpyHostToDevice, st) != cudaSuccess)
+      return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: upload failed"));
     simt::f64_to_f32_kernel<<<ceil_div(3 * m, 256), 256, 0, st>>>((const double*)(w + o_p64), (float*)(w + o_p32), 3 * m);
     DJ_LAUNCHED();
-    int rc = run_forward(p, (const float*)(w + o_code), (const float*)(w + o_p32), GridSpec{}, m, H, net_mask_for(use_net),
-                         precision, (float*)(w + o_o32), st);
-    if (rc) return rc;
+    int rc = run_forward(p, (const float*)w0, (const float*)(w + o_p32), GridSpec{}, m, H, net_mask_for(use_net),
+                         precision, (float*)(w + o_o32), st, false);
+    if (rc) return cleanup(rc);
     simt::f32_to_f64_kernel<<<ceil_div(m, 256), 256, 0, st>>>((const float*)(w + o_o32), (double*)(w + o_o64), m);
     DJ_LAUNCHED();
-    DJ_CUDA(cudaMemcpyAsync(out_host + s, w + o_o64, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+    if (cudaMemcpyAsync(out_host + s, w + o_o64, (size_t)m * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+      return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: download failed"));
   }
-  DJ_CUDA(cudaStreamSynchronize(st));
-  if (precision == DJ_PREC_BF16) return check_err_word(p, st);
+  int rc = cleanup(DJ_OK);
+  if (rc) return rc;
+  if (precision == DJ_PREC_BF16) return check_err_word(p, 0);
   return DJ_OK;
 }
 
