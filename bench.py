@@ -158,7 +158,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", type=int, default=256)
     ap.add_argument("--use-net", type=int, default=1)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--query-only", action="store_true", help="diagnostics: time the grid query alone (not a bench line)")
     ap.add_argument("--latent-shapes", type=int, default=8,
@@ -353,7 +353,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": "configs[1]: single-shape dense query + marching cubes at %d^3 grid per GPU, "
                                    "use_net=%d, padding 0.1, level 0 ascent; synthetic trained-norm weights" % (d, u),
                        "l2": "256 MB flush buffer written before every step (inside the timed bracket)",
@@ -367,8 +367,8 @@ def main():
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 launch (ncu --set full,
                          # profiles/r01_tc2_forward_256_ncu_full.txt): 6.2 MB of weights + 16.6 MB of the 67 MB
                          # output volume (the rest is still in L2 when the kernel ends)
-                         "traffic": 22831616 if (args.precision == "bf16" and d == 256) else None,
-                         "kernel": "tc2_forward_kernel" if args.precision == "bf16" else "sgemm_kernel",
+                         "traffic": 22831616 if (args.precision != "fp32" and d == 256) else None,
+                         "kernel": "tc2_forward_kernel" if args.precision != "fp32" else "sgemm_kernel",
                          "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step); burst %.1f" % (which, burst),
                          "flop_per_query": FLOP_ALG[u]},
             "clocks": clocks,

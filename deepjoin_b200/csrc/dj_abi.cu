@@ -31,6 +31,7 @@ struct DjPack {
   tc::TcNet nets[2];
   // CTA-pair (cta_group::2) program: one weight stream per cluster rank
   uint8_t* stream2[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  uint8_t* stream2h[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // the same stages with IEEE-half weights (DJ_PREC_FP16)
   tc2::Net nets2[2];
   unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
   // fused forward+backward program of the latent step (latent_tc2.cuh)
@@ -60,6 +61,8 @@ static void free_pack(DjPack* p) {
     if (p->stream[i]) cudaFree(p->stream[i]);
     for (int r = 0; r < 2; r++)
       if (p->stream2[i][r]) cudaFree(p->stream2[i][r]);
+    for (int r = 0; r < 2; r++)
+      if (p->stream2h[i][r]) cudaFree(p->stream2h[i][r]);
   }
   if (p->bias_dev) cudaFree(p->bias_dev);
   for (int r = 0; r < 2; r++)
@@ -77,14 +80,19 @@ static void free_pack(DjPack* p) {
 
 // one [rows x 64] bf16 tile, K-major, 128-byte swizzle (the layout the UMMA descriptor
 // umma_desc_sw128_kmajor describes): element (r, k) at r*128 + ((k/8) ^ (r%8))*16 + (k%8)*2
-static void pack_tile(const float* W, int ldw, int n_real, int k_real, int n0, int k0, int rows, uint8_t* dst) {
+static void pack_tile(const float* W, int ldw, int n_real, int k_real, int n0, int k0, int rows, uint8_t* dst, bool f16 = false) {
   for (int r = 0; r < rows; r++)
     for (int k = 0; k < 64; k++) {
       const int gn = n0 + r, gk = k0 + k;
       const float v = (gn < n_real && gk < k_real) ? W[(size_t)gn * ldw + gk] : 0.f;
-      const __nv_bfloat16 b = __float2bfloat16_rn(v);
       const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
-      memcpy(dst + off, &b, 2);
+      if (f16) {
+        const __half b = __float2half_rn(v);
+        memcpy(dst + off, &b, 2);
+      } else {
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        memcpy(dst + off, &b, 2);
+      }
     }
 }
 
@@ -265,7 +273,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     N.n_layers = N1.n_layers;
     N.l0_table = N1.l0_table;
     N.head_leaky = N1.head_leaky;
-    std::vector<uint8_t> blob[2];
+    std::vector<uint8_t> blob[2], blobh[2];
     for (int l = 1; l < nl; l++) {
       const tc::TcLayer& T1 = N1.layers[l - 1];
       tc2::Layer& T = N.layers[l - 1];
@@ -289,12 +297,16 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
             for (int kc = 0; kc < 2; kc++) {
               const size_t o = blob[r].size();
               blob[r].resize(o + T.tile_bytes);
+              blobh[r].resize(o + T.tile_bytes);
               pack_tile(W[l], ins[l], n_real, k_real, j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blob[r].data() + o);
+              pack_tile(W[l], ins[l], n_real, k_real, j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blobh[r].data() + o, true);
             }
     }
     for (int r = 0; r < 2; r++) {
       DJ_TRY(cudaMalloc((void**)&p->stream2[net][r], blob[r].size()));
       DJ_TRY(cudaMemcpy(p->stream2[net][r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
+      DJ_TRY(cudaMalloc((void**)&p->stream2h[net][r], blobh[r].size()));
+      DJ_TRY(cudaMemcpy(p->stream2h[net][r], blobh[r].data(), blobh[r].size(), cudaMemcpyHostToDevice));
       N.stream[r] = p->stream2[net][r];
     }
   }
@@ -473,11 +485,16 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
   if (n <= 0) return DJ_OK;
   int rc;
   if (do_fold && (rc = launch_fold(p, code_dev, st))) return rc;
-  if (precision == DJ_PREC_BF16 && p->tc_kernel == 2) {
+  if (precision == DJ_PREC_FP16 && p->tc_kernel != 2) return fail(DJ_ERR_UNSUPPORTED, "DJ_PREC_FP16 needs the CTA-pair kernel (DEEPJOIN_B200_TC=2)");
+  if ((precision == DJ_PREC_BF16 || precision == DJ_PREC_FP16) && p->tc_kernel == 2) {
+    const bool f16 = precision == DJ_PREC_FP16;
     tc2::Params P;
     memset(&P, 0, sizeof P);
     P.nets[0] = p->nets2[0];
     P.nets[1] = p->nets2[1];
+    if (f16)
+      for (int net = 0; net < 2; net++)
+        for (int r = 0; r < 2; r++) P.nets[net].stream[r] = p->stream2h[net][r];
     P.net_mask = net_mask;
     P.grid_mode = G.on;
     if (const char* e = getenv("DEEPJOIN_B200_DEBUG")) P.debug = atoi(e);
@@ -495,12 +512,14 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     const int64_t ntiles = (n + tc2::TILE_M - 1) / tc2::TILE_M;
     const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);  // whole CTA pairs
     if (!p->tc_attr_set2) {
-      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       p->tc_attr_set2 = true;
     }
-    if (P.debug) tc2::tc2_forward_kernel<1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
-    else tc2::tc2_forward_kernel<0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    else if (P.debug) tc2::tc2_forward_kernel<1, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    else tc2::tc2_forward_kernel<0, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     DJ_LAUNCHED();
     return DJ_OK;
   }
@@ -653,7 +672,7 @@ extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const d
   for (int64_t s = 0; s < n; s += CH, k++) {
     const int64_t m = std::min(CH, n - s);
     // the fp32 path works in one shared activation workspace: it stays on one stream
-    const int lane = (precision == DJ_PREC_BF16) ? (k & 1) : 0;
+    const int lane = (precision != DJ_PREC_FP32) ? (k & 1) : 0;
     cudaStream_t st = sts[lane];
     uint8_t* w = w0 + 1024 + (size_t)lane * half;
     if (cudaMemcpyAsync(w + o_p64, pts_host + 3 * s, (size_t)m * 24, cudaMemcpyHostToDevice, st) != cudaSuccess)
@@ -670,7 +689,7 @@ extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const d
   }
   int rc = cleanup(DJ_OK);
   if (rc) return rc;
-  if (precision == DJ_PREC_BF16) return check_err_word(p, 0);
+  if (precision != DJ_PREC_FP32) return check_err_word(p, 0);
   return DJ_OK;
 }
 
@@ -832,7 +851,8 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
 
 static int check_latent_cfg(DjPack* p, const DjLatentCfg* cfg) {
   if (!cfg) return fail(DJ_ERR_INVALID, "null DjLatentCfg");
-  if (cfg->precision != DJ_PREC_FP32 && cfg->precision != DJ_PREC_BF16) return fail(DJ_ERR_INVALID, "latent gradient: unknown precision %d", cfg->precision);
+  if (cfg->precision != DJ_PREC_FP32 && cfg->precision != DJ_PREC_BF16 && cfg->precision != DJ_PREC_FP16)
+    return fail(DJ_ERR_INVALID, "latent gradient: unknown precision %d", cfg->precision);
   if (p->L + p->Lb > 256) return fail(DJ_ERR_UNSUPPORTED, "code length > 256");
   return DJ_OK;
 }
@@ -845,7 +865,7 @@ extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz
   if ((rc = check_latent_cfg(p, cfg))) return rc;
   DeviceGuard g(p->device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (cfg->precision == DJ_PREC_BF16) {
+  if (cfg->precision != DJ_PREC_FP32) {  // tensor cores (bf16 operands; gradients underflow in IEEE half)
     LatTcWs T;
     if ((rc = carve_latent_tc(p, 1, T))) return rc;
     if ((rc = upload_ptrs(T, 1, &xyz_dev, &sdf_dev, &nrm_dev, st))) return rc;
@@ -882,7 +902,7 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
   const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
   const int64_t log_rows = (cfg->num_iterations + log_every - 1) / log_every;
   simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations};
-  if (cfg->precision == DJ_PREC_BF16) {
+  if (cfg->precision != DJ_PREC_FP32) {
     // all shapes in one launch per iteration; the kernel gathers every shape's mini-batch rows itself
     LatTcWs T;
     if ((rc = carve_latent_tc(p, n_shapes, T))) return rc;
@@ -1141,7 +1161,7 @@ extern "C" int dj_create_mesh_count(DjPack* p, DjMcWork* w, const float* code_ho
   if (rc) return rc;
   // values.reshape(dims): the flat rows are reinterpreted as a C-contiguous [d0, d1, d2] volume (core/reconstruct.py:162)
   rc = dj_mc_count(w, vol, d0, d1, d2, 0, 0, level, 1, n_verts, n_faces, st);
-  if (precision == DJ_PREC_BF16) {
+  if (precision != DJ_PREC_FP32) {
     int rc2 = check_err_word(p, st);
     if (rc2) return rc2;
   }

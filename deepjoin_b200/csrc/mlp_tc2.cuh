@@ -103,7 +103,8 @@ __device__ __forceinline__ void grid_point(const Params& P, int64_t r, float& x,
 
 // DBG = 1 compiles the bench diagnostics in (Params::debug knobs and cycle counters); the product path
 // launches DBG = 0.
-template <int DBG>
+// F16 = 1: IEEE-half operands (DJ_PREC_FP16) instead of bf16 -- same instruction, same speed, 8x finer rounding.
+template <int DBG, int F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_forward_kernel(const __grid_constant__ Params P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -221,7 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
         const int nl = N.n_layers;
         for (int l = 0; l < nl; l++) {
           const int n_chunks = N.layers[l].n_chunks, k_stages = N.layers[l].k_stages;
-          const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)N.layers[l].mma_n);
+          const uint32_t idesc = F16 ? ptx::umma_idesc_f16(256, (uint32_t)N.layers[l].mma_n) : ptx::umma_idesc_bf16(256, (uint32_t)N.layers[l].mma_n);
           const uint32_t tile16 = (uint32_t)N.layers[l].tile_bytes >> 4;
           const int src = l & 1;
           for (int j = 0; j < n_chunks; j++) {
@@ -346,8 +347,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
               const float4 t = sTab[c * 64 + gq * 8 + f];
               v[f] = tc::leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
             }
-            tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_bf16x2(v[0], v[1]),
-                             ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+            tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_op16x2<F16>(v[0], v[1]),
+                             ptx::pack_op16x2<F16>(v[2], v[3]), ptx::pack_op16x2<F16>(v[4], v[5]), ptx::pack_op16x2<F16>(v[6], v[7]));
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();
@@ -421,7 +422,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                   const float4 t0 = sTab[col0 + gq * 8 + f], t1 = sTab[col0 + gq * 8 + f + 1];
                   const float v0 = tc::leaky(__uint_as_float(r[gq * 8 + f]) + fmaf(t0.x, x, fmaf(t0.y, y, fmaf(t0.z, z, t0.w))), slope);
                   const float v1 = tc::leaky(__uint_as_float(r[gq * 8 + f + 1]) + fmaf(t1.x, x, fmaf(t1.y, y, fmaf(t1.z, z, t1.w))), slope);
-                  pk[gq * 4 + (f >> 1)] = ptx::pack_bf16x2(v0, v1);
+                  pk[gq * 4 + (f >> 1)] = ptx::pack_op16x2<F16>(v0, v1);
                 }
               } else {
                 const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
@@ -433,7 +434,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                   const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
                   const uint64_t t = ptx::add_f32x2(acc, bb[f]);       // FADD2
                   const uint64_t u = ptx::mul_f32x2(t, slope2);        // FMUL2
-                  pk[gq * 4 + f] = ptx::pack_bf16x2(fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u)), fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u)));
+                  pk[gq * 4 + f] = ptx::pack_op16x2<F16>(fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u)), fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u)));
                 }
               }
               if (DST == 0)

@@ -319,6 +319,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(uint32_t m, uint32_t n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
+// same with IEEE-half operands (a_format = b_format = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+
 // packed fp32 pairs (FADD2 / FMUL2 / FFMA2 on sm_100)
 __device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
   return (uint64_t)__float_as_uint(lo) | ((uint64_t)__float_as_uint(hi) << 32);
@@ -336,12 +341,28 @@ __device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
 __device__ __forceinline__ float f32x2_lo(uint64_t v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float f32x2_hi(uint64_t v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
+// packed f16x2 from two floats (lo -> low half), saturating to the largest finite half
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// 16-bit operand pair of the tensor-core path: bf16 (F16 = 0) or IEEE half (F16 = 1, 3 more mantissa bits,
+// activations of this decoder are far inside its range)
+template <int F16>
+__device__ __forceinline__ uint32_t pack_op16x2(float lo, float hi);
+
 // packed bf16x2 from two floats (lo -> low half)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+
+template <>
+__device__ __forceinline__ uint32_t pack_op16x2<0>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <>
+__device__ __forceinline__ uint32_t pack_op16x2<1>(float lo, float hi) { return pack_f16x2(lo, hi); }
 
 }  // namespace ptx
 }  // namespace dj

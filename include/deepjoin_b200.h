@@ -36,6 +36,8 @@ extern "C" {
 /* arithmetic of the hidden layers */
 #define DJ_PREC_FP32 0   /* fp32 CUDA-core path: the reference's own arithmetic (torch fp32 SGEMM) */
 #define DJ_PREC_BF16 1   /* bf16 operands, fp32 accumulation in TMEM, tcgen05 tensor cores         */
+#define DJ_PREC_FP16 2   /* IEEE-half operands on the same kernels (forward only): same speed, 8x finer
+                            operand rounding than bf16; the latent step treats it as DJ_PREC_BF16  */
 
 /* use_net selector of Decoder.forward (networks/decoder_z_lb_both_leaky_n_sdf.py:345-453) */
 #define DJ_NET_C 0

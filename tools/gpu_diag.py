@@ -81,6 +81,12 @@ def stage_tc():
     return {k: _fwd_errors("bf16", k) for k in ("default", "trained_norm")}
 
 
+def stage_fp16():
+    """IEEE-half operands on the pair kernel (DJ_PREC_FP16) vs bf16: error against the fp64 oracle."""
+    return {"fp16": {k: _fwd_errors("fp16", k) for k in ("default", "trained_norm")},
+            "bf16": {k: _fwd_errors("bf16", k) for k in ("default", "trained_norm")}}
+
+
 def stage_mc():
     import numpy as np
     import torch
@@ -250,7 +256,7 @@ def stage_prof():
     return out
 
 
-STAGES = {"prof": stage_prof, "latent_timing": stage_latent_timing, "latent_tc": stage_latent_tc, "probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
+STAGES = {"fp16": stage_fp16, "prof": stage_prof, "latent_timing": stage_latent_timing, "latent_tc": stage_latent_tc, "probe": stage_probe, "fp32": stage_fp32, "mc": stage_mc, "latent": stage_latent, "tc": stage_tc,
           "timing": stage_timing}
 
 if __name__ == "__main__":
