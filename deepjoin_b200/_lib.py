@@ -53,6 +53,7 @@ SIGNATURES = {
                                    ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "dj_create_mesh_fetch": (c_i, [c_p, c_p, c_p]),
     "dj_mesh_merge_vertices": (c_i, [c_p, c_p, c_i64, c_p, c_i64, ctypes.POINTER(c_i64), c_p]),
+    "dj_nn_query": (c_i, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p]),
     "dj_debug_umma_probe": (c_i, [c_p, c_p, c_i, c_i, c_i, ctypes.c_uint32, ctypes.c_uint64, c_p]),
     "dj_debug_read_prof": (c_i, [c_p, c_p, c_i]),
     "dj_launch_count": (c_i64, [c_i]),

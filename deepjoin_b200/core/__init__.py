@@ -3,7 +3,7 @@
 grid query / meshing)."""
 from . import errors  # noqa: F401  (first: _lib imports it)
 from .errors import *  # noqa: F401,F403
-from . import data, reconstruct, utils_multiprocessing, utils_deepsdf  # noqa: F401,E402
+from . import data, metrics, reconstruct, utils_multiprocessing, utils_deepsdf  # noqa: F401,E402
 from .reconstruct import (create_mesh, decode_samples, decode_shape, get_query_points,  # noqa: F401,E402
                           tensor_sdf_to_occ, tensor_sdf_to_udf, tensor_udf_to_sdf)
 from .data import select_samples, clamp_samples  # noqa: F401,E402

@@ -8,6 +8,7 @@
 #include "mc.cuh"
 #include "sampler.cuh"
 #include "mesh_merge.cuh"
+#include "nn.cuh"
 #include "debug_probe.cuh"
 
 using namespace dj;
@@ -1196,6 +1197,17 @@ extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* fa
   DJ_CUDA(cudaMemcpyAsync(verts_host, w->v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaMemcpyAsync(faces_host, w->faces.as<int>(), (size_t)w->nf * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaStreamSynchronize(st));
+  return DJ_OK;
+}
+
+// ====================================================================== evaluation metrics: nearest neighbour
+extern "C" int dj_nn_query(const float* queries_dev, int64_t n, const float* targets_dev, int64_t m, float* dist2_dev,
+                           int32_t* idx_dev, void* stream) {
+  if (n < 0 || m < 1 || (n && (!queries_dev || !dist2_dev || !idx_dev)) || !targets_dev || m > 0x7fffffffll)
+    return fail(DJ_ERR_INVALID, "dj_nn_query: bad argument");
+  if (n == 0) return DJ_OK;
+  nn::nn_kernel<<<(unsigned)ceil_div(n, (int64_t)nn::QB), nn::QB, 0, (cudaStream_t)stream>>>(queries_dev, targets_dev, n, m, dist2_dev, idx_dev);
+  DJ_LAUNCHED();
   return DJ_OK;
 }
 

@@ -194,6 +194,12 @@ int dj_create_mesh_fetch(DjMcWork* work, double* verts_host, int32_t* faces_host
 int dj_mesh_merge_vertices(DjMcWork* work, double* verts_dev, int64_t n_verts, int32_t* faces_dev, int64_t n_faces,
                            int64_t* n_verts_out, void* stream);
 
+/* replaces: scipy.spatial.cKDTree(targets).query(queries) of the evaluation metrics that follow meshing
+ * (core/metrics.py:46-50,79): exact nearest neighbour by brute force on the current device.
+ * queries [n,3], targets [m,3] f32; dist2 [n] squared distances, idx [n] int32 (smallest index on ties). */
+int dj_nn_query(const float* queries_dev, int64_t n, const float* targets_dev, int64_t m, float* dist2_dev,
+                int32_t* idx_dev, void* stream);
+
 /* DEBUG ONLY (tools/gpu_diag.py): one 128x128xK bf16 UMMA built from the product kernel's pieces;
  * D_host [128,128] = bf16(A_host [128,K]) . bf16(W_host [128,K])^T.  Zero for k_adv_bytes / idesc /
  * desc_tmpl selects the product encodings. */
