@@ -1,5 +1,6 @@
-"""Worker-side glue of the reference's ``core/utils_multiprocessing.py:16-114`` with the same
-names and keyword arguments: one decoder (and CUDA context) per worker process."""
+"""Worker-side glue with the call surface of the reference's ``core/utils_multiprocessing.py:16-114``
+(``load_network``, ``reconstruct_chunk``, ``mesh_chunk``: same names, keyword arguments, skip / overwrite rules
+and error handling), one decoder and one CUDA context per worker process."""
 import logging
 import os
 
@@ -9,79 +10,87 @@ import torch
 from deepjoin_b200.mesh import Mesh
 from . import errors
 
-model_params_subdir = "ModelParameters"  # core/workspace.py:8
+model_params_subdir = "ModelParameters"  # experiment layout, core/workspace.py:8
+_log = logging.getLogger(__name__)
 
 
 def file_is_old(path, overwrite_time=1636410000):
-    """core/utils.py:6-18."""
-    if overwrite_time is None:
-        return False
-    return os.path.exists(path) and os.path.getmtime(path) < overwrite_time
+    """A result written before ``overwrite_time`` counts as missing (core/utils.py:6-18)."""
+    return overwrite_time is not None and os.path.exists(path) and os.path.getmtime(path) < overwrite_time
 
 
 def lossify_log_path(path):
-    """core/handler.py:617-619."""
-    p, e = os.path.splitext(path)
-    return p + "__loss" + e
+    """``a/b.pth`` -> ``a/b__loss.pth`` (core/handler.py:617-619)."""
+    stem, ext = os.path.splitext(path)
+    return stem + "__loss" + ext
 
 
 def load_network(decoder_kwargs, decoder_constructor, experiment_directory, checkpoint):
-    """core/utils_multiprocessing.py:16-30.  The checkpoint's ``module.`` prefix (DataParallel)
-    is accepted by Decoder.load_state_dict directly."""
+    """core/utils_multiprocessing.py:16-30.  The reference wraps the decoder in DataParallel only to match the
+    checkpoint's ``module.`` key prefix; ``Decoder.load_state_dict`` here strips that prefix itself."""
+    ckpt = os.path.join(experiment_directory, model_params_subdir, checkpoint + ".pth")
+    state = torch.load(ckpt, map_location="cpu", weights_only=False)["model_state_dict"]
     decoder = decoder_constructor(**decoder_kwargs)
-    saved_model_state = torch.load(
-        os.path.join(experiment_directory, model_params_subdir, checkpoint + ".pth"),
-        map_location="cpu", weights_only=False)
-    decoder.load_state_dict(saved_model_state["model_state_dict"])
-    decoder = decoder.cuda()
-    decoder.eval()
-    return decoder
+    decoder.load_state_dict(state)
+    return decoder.cuda().eval()
+
+
+def _todo(path, overwrite):
+    return overwrite or not os.path.exists(path) or file_is_old(path)
+
+
+def _each(chunk_inputs, chunk_paths, overwrite, callback, work):
+    """The shared item loop of both workers: skip finished items, report progress."""
+    for item, path in zip(chunk_inputs, chunk_paths):
+        if _todo(path, overwrite):
+            work(item, path)
+        else:
+            _log.debug("Skipping %s", path)
+        if callback is not None:
+            callback()
 
 
 def reconstruct_chunk(chunk_inputs, chunk_paths, reconstruct_fn, network_kwargs, reconstruction_kwargs,
                       overwrite=False, callback=None, save=True):
-    """core/utils_multiprocessing.py:33-71."""
+    """core/utils_multiprocessing.py:33-71: latent code + loss log per item (``Codes/<idx>_<sig>.pth``,
+    ``...__loss.npy``)."""
     decoder = load_network(**network_kwargs)
-    decoder.eval()
-    for input, path in zip(chunk_inputs, chunk_paths):
-        if overwrite or not os.path.exists(path) or file_is_old(path):
-            loss, latent = reconstruct_fn(decoder=decoder, **input, **reconstruction_kwargs)
-            try:
-                if save:
-                    logging.debug("Reconstruct chunker saving to: {}".format(path))
-                    torch.save(latent, path)
-                    np.save(lossify_log_path(path), loss)
-            except PermissionError:
-                logging.warning("Could not save: {}".format(path))
-        else:
-            logging.debug("Skipping {}".format(path))
-        if callback is not None:
-            callback()
+
+    def work(item, path):
+        loss, latent = reconstruct_fn(decoder=decoder, **item, **reconstruction_kwargs)
+        if not save:
+            return
+        try:
+            _log.debug("Reconstruct chunker saving to: %s", path)
+            torch.save(latent, path)
+            np.save(lossify_log_path(path), loss)
+        except PermissionError:
+            _log.warning("Could not save: %s", path)
+
+    _each(chunk_inputs, chunk_paths, overwrite, callback, work)
 
 
 def mesh_chunk(chunk_inputs, chunk_paths, mesh_fn, network_kwargs, mesh_kwargs, overwrite=False, callback=None,
                save=True):
-    """core/utils_multiprocessing.py:74-114: IsosurfaceExtractionError -> empty mesh."""
+    """core/utils_multiprocessing.py:74-114: one mesh file per item; an IsosurfaceExtractionError becomes an
+    empty mesh (:96-98), a PermissionError is logged and the item skipped."""
     decoder = load_network(**network_kwargs)
-    decoder.eval()
-    for input, path in zip(chunk_inputs, chunk_paths):
-        if overwrite or not os.path.exists(path) or file_is_old(path):
+
+    def work(item, path):
+        try:
+            with torch.no_grad():
+                mesh = mesh_fn(decoder=decoder, **item, **mesh_kwargs)
+        except errors.IsosurfaceExtractionError:
+            _log.debug("Isosurface extraction error on sample: %s", path)
+            mesh = Mesh()
+        except PermissionError:
+            _log.warning("Could not save: %s", path)
+            return
+        if save:
             try:
-                with torch.no_grad():
-                    mesh = mesh_fn(decoder=decoder, **input, **mesh_kwargs)
-            except errors.IsosurfaceExtractionError:
-                mesh = Mesh()
-                logging.debug("Isosurface extraction error on sample: {}".format(path))
+                _log.debug("Mesh chunker saving to: %s", path)
+                mesh.export(path)
             except PermissionError:
-                mesh = None
-                logging.warning("Could not save: {}".format(path))
-            try:
-                if save and mesh is not None:
-                    logging.debug("Mesh chunker saving to: {}".format(path))
-                    mesh.export(path)
-            except PermissionError:
-                logging.warning("Could not save: {}".format(path))
-        else:
-            logging.debug("Skipping {}".format(path))
-        if callback is not None:
-            callback()
+                _log.warning("Could not save: %s", path)
+
+    _each(chunk_inputs, chunk_paths, overwrite, callback, work)
