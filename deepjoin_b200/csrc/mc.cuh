@@ -26,6 +26,8 @@ namespace dj {
 namespace mc {
 
 constexpr int CB = 256;  // cells per block
+// variants of the two configurations without a surface (DJ_MC_VARBASE[0], DJ_MC_VARBASE[255]; no ambiguous faces)
+constexpr int DJ_MC_VAR_EMPTY0 = 0, DJ_MC_VAR_EMPTY255 = 655;
 // edges that are owned only on the x==0 / y==0 / z==0 boundary of the slab
 constexpr unsigned MX = 0x988, MY = 0x311, MZ = 0x00F;
 constexpr double FLT_EPS_D = 1.1920928955078125e-07;
@@ -51,13 +53,15 @@ __device__ __forceinline__ bool block_cell(const Dims& D, int t, int& zr, int& y
 }
 __device__ __forceinline__ int64_t block_linear() { return (int64_t)blockIdx.y * gridDim.x + blockIdx.x; }
 
+// corner i of the cell at (z, y, x): Lewiner's numbering (0,0,0) (1,0,0) (1,1,0) (0,1,0) and the same at z+1 --
+// the order of DJ_MC_CORNER, written out so that the eight loads are one base address plus constant offsets
 __device__ __forceinline__ void load_cube(const Dims& D, const float* __restrict__ vol, int zr, int y, int x, double (&f)[8]) {
-  const int z = zr;
+  const int64_t sy = D.n2, sz = (int64_t)D.n1 * D.n2;
+  const float* p = vol + ((int64_t)zr * D.n1 + y) * D.n2 + x;
+  const float v[8] = {__ldg(p), __ldg(p + 1), __ldg(p + sy + 1), __ldg(p + sy),
+                      __ldg(p + sz), __ldg(p + sz + 1), __ldg(p + sz + sy + 1), __ldg(p + sz + sy)};
 #pragma unroll
-  for (int i = 0; i < 8; i++) {
-    const int dx = DJ_MC_CORNER[i][0], dy = DJ_MC_CORNER[i][1], dz = DJ_MC_CORNER[i][2];
-    f[i] = __dsub_rn((double)__ldg(vol + ((int64_t)(z + dz) * D.n1 + (y + dy)) * D.n2 + (x + dx)), D.level);
-  }
+  for (int i = 0; i < 8; i++) f[i] = __dsub_rn((double)v[i], D.level);
 }
 
 __device__ __forceinline__ int cube_variant(const double (&f)[8]) {
@@ -145,10 +149,18 @@ __global__ void __launch_bounds__(CB) classify_kernel(Dims D, const float* __res
   if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
     double f[8];
     load_cube(D, vol, zr, y, x, f);
-    const int var = cube_variant(f);
-    var_out[ci] = (uint16_t)var;
-    nt = DJ_MC_NTRI[var];
-    if (nt) nv = owned_count(var, owned_mask(D, zr, y, x));
+    int cfg = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) cfg |= (f[i] > 0.0) ? (1 << i) : 0;
+    if (cfg == 0 || cfg == 255) {
+      // ~97 % of the cells: not cut by the surface -- no table look-ups (their variants have no triangles)
+      var_out[ci] = (uint16_t)(cfg == 0 ? DJ_MC_VAR_EMPTY0 : DJ_MC_VAR_EMPTY255);
+    } else {
+      const int var = cube_variant(f);
+      var_out[ci] = (uint16_t)var;
+      nt = DJ_MC_NTRI[var];
+      if (nt) nv = owned_count(var, owned_mask(D, zr, y, x));
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {

@@ -183,3 +183,14 @@ def test_seam_mode_leaves_only_plane0_references_open():
     seam_ids = {i for (z, y, x, d), i in _parallel_mc.last_edge_id.items() if z == 0 and d in (0, 1)}
     assert nv == nv_full - len(seam_ids) and pf.shape == pf_full.shape
     assert ((pf == -1) == np.isin(pf_full, list(seam_ids))).all()
+
+
+def test_kernel_shortcut_constants_match_the_tables():
+    """classify_kernel skips the table look-ups for cells the surface does not cut: its two hard-wired variant ids
+    must be the tables' (and triangle-free)."""
+    import re
+    var_base, n_amb, amb_faces, variants = T.build()
+    src = open(os.path.join(ROOT, "deepjoin_b200", "csrc", "mc.cuh")).read()
+    m = re.search(r"DJ_MC_VAR_EMPTY0 = (\d+), DJ_MC_VAR_EMPTY255 = (\d+)", src)
+    assert (int(m.group(1)), int(m.group(2))) == (var_base[0], var_base[255])
+    assert len(variants[var_base[0]][0]) == 0 and len(variants[var_base[255]][0]) == 0 and n_amb[0] == 0 and n_amb[255] == 0
