@@ -1013,6 +1013,7 @@ extern "C" int dj_mc_count(DjMcWork* w, const float* vol_dev, int n0, int n1, in
     DJ_LAUNCHED();
   }
   const dim3 mc_grid((unsigned)w->bpp, (unsigned)(n0 - 1));
+  DJ_CUDA(cudaMemsetAsync(w->counts.as<int2>(), 0, (size_t)w->nblocks * sizeof(int2), st));
   mc::classify_kernel<<<mc_grid, mc::CB, 0, st>>>(D, vol_dev, w->var.as<uint16_t>(), w->counts.as<int2>());
   DJ_LAUNCHED();
   mc::scan_groups_kernel<<<(unsigned)ngroups, mc::SG, 0, st>>>(w->counts.as<int2>(), w->nblocks, w->offs.as<int2>(), group_off);
@@ -1055,9 +1056,9 @@ extern "C" int dj_mc_fill(DjMcWork* w, int descent, float* verts_dev, int32_t* f
   }
   const dim3 mc_grid((unsigned)w->bpp, (unsigned)(D.n0 - 1));
   const longlong2* group_off = reinterpret_cast<const longlong2*>(w->misc.as<long long>() + 8);
-  mc::emit_vertices_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->vol, w->var.as<uint16_t>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), verts_dev);
+  mc::emit_vertices_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->vol, w->var.as<uint16_t>(), w->counts.as<int2>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), verts_dev);
   DJ_LAUNCHED();
-  mc::emit_faces_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->var.as<uint16_t>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), descent, faces_dev);
+  mc::emit_faces_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->var.as<uint16_t>(), w->counts.as<int2>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), descent, faces_dev);
   DJ_LAUNCHED();
   return DJ_OK;
 }
