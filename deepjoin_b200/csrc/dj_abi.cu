@@ -98,6 +98,28 @@ static void pack_tile(const float* W, int ldw, int n_real, int k_real, int n0, i
 }
 
 
+// layer-0 tile: row n (hidden unit), K = 16 slots [W_xyz(3) | W_xyz(3) | lo(W_xyz)(3) | 0] in the operand type,
+// against the point operand [p_hi | p_lo | p_hi | 0] (mlp_tc2.cuh): sum = W_hi (p_hi + p_lo) + W_lo p_hi
+static void pack_tile_l0(const float* W, int ldw, int xyz_off, int n0, int rows, uint8_t* dst, bool f16) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      float v = 0.f;
+      if (k < 9) {
+        const float w = W[(size_t)(n0 + r) * ldw + xyz_off + k % 3];
+        const float hi = f16 ? __half2float(__float2half_rn(w)) : __bfloat162float(__float2bfloat16_rn(w));
+        v = (k < 6) ? hi : (w - hi);
+      }
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      if (f16) {
+        const __half b = __float2half_rn(v);
+        memcpy(dst + off, &b, 2);
+      } else {
+        const __nv_bfloat16 b = __float2bfloat16_rn(v);
+        memcpy(dst + off, &b, 2);
+      }
+    }
+}
+
 // transposed source: tile row n, column k <- W[k0 + k][n0 + n]  (B operand of a backward GEMM, dX = dY . W)
 static void pack_tile_T(const float* W, int ldw, int out_real, int in_real, int n0, int k0, int rows, uint8_t* dst) {
   for (int r = 0; r < rows; r++)
@@ -261,8 +283,9 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     DJ_TRY(cudaMemcpy(p->stream[net], blob.data(), blob.size(), cudaMemcpyHostToDevice));
     N.stream = p->stream[net];
   }
-  // ---- CTA-pair program: same layers / bias offsets; every 128-row output chunk is split 64/64 between the
-  // two CTAs of a pair and a ring stage carries K = 128 (two [rows x 64] tiles)
+  // ---- CTA-pair program: layer 0 as a K = 16 tensor-core layer (point split hi/lo), then the same layers / bias
+  // offsets; every 128-row output chunk is split 64/64 between the two CTAs of a pair and a ring stage carries
+  // K = 128 (two [rows x 64] tiles)
   for (int net = 0; net < 2; net++) {
     const int nl = net == 0 ? d->f_layers : d->h_layers;
     const float* const* W = net == 0 ? f_w : h_w;
@@ -271,13 +294,28 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     const tc::TcNet& N1 = p->nets[net];
     tc2::Net& N = p->nets2[net];
     memset(&N, 0, sizeof N);
-    N.n_layers = N1.n_layers;
+    N.n_layers = N1.n_layers + 1;
     N.l0_table = N1.l0_table;
     N.head_leaky = N1.head_leaky;
+    if (N.n_layers > tc2::MAX_LAYERS) return bail(fail(DJ_ERR_UNSUPPORTED, "too many layers for the CTA-pair program"));
     std::vector<uint8_t> blob[2], blobh[2];
+    {
+      tc2::Layer& T = N.layers[0];
+      T.n_chunks = 4; T.k_stages = 1; T.k_steps = 1; T.mma_n = 128; T.kind = tc2::KIND_L0TC;
+      T.tile_bytes = 64 * 128; T.stage_bytes = T.tile_bytes;
+      const int xyz_off = (net == 0 ? L : Lb);
+      for (int j = 0; j < 4; j++)
+        for (int r = 0; r < 2; r++) {
+          const size_t o = blob[r].size();
+          blob[r].resize(o + T.tile_bytes);
+          blobh[r].resize(o + T.tile_bytes);
+          pack_tile_l0(W[0], ins[0], xyz_off, j * 128 + r * 64, 64, blob[r].data() + o, false);
+          pack_tile_l0(W[0], ins[0], xyz_off, j * 128 + r * 64, 64, blobh[r].data() + o, true);
+        }
+    }
     for (int l = 1; l < nl; l++) {
       const tc::TcLayer& T1 = N1.layers[l - 1];
-      tc2::Layer& T = N.layers[l - 1];
+      tc2::Layer& T = N.layers[l];
       const bool head = (l == nl - 1);
       const bool reinj = (net == 0 && l == li);
       const int n_real = outs[l];
@@ -285,6 +323,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       if (T1.k_chunks % 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K chunks must be even", l));
       T.n_chunks = T1.n_chunks;
       T.k_stages = (int16_t)(T1.k_chunks / 2);
+      T.k_steps = 8;
       T.mma_n = (int16_t)(head ? 32 : 128);
       T.kind = T1.kind;
       T.bias_off = T1.bias_off;
@@ -352,7 +391,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       add(lat2::K_L0, 2, 0, 0, 0, 0, 0, mask++, net == 0 ? 0 : 2, 0, 0);
       buf = 0;
       for (int l = 1; l < nl; l++) {
-        const tc2::Layer& F = N2.layers[l - 1];
+        const tc2::Layer& F = N2.layers[l];
         const bool head = (l == nl - 1);
         const bool reinj = (net == 0 && l == li);
         const int k_real = reinj ? K3 : ins[l];

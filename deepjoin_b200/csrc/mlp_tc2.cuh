@@ -63,7 +63,9 @@ struct Layer {
   int32_t table;      // xyzw table id (KIND_HIDDEN_XYZ)
   int32_t stage_bytes;  // per CTA
   int32_t tile_bytes;   // one [mma_n/2 x 64] tile
+  int32_t k_steps;      // MMAs per ring stage: 8 (K = 128), or 1 for the K = 16 operand of layer 0
 };
+constexpr int KIND_L0TC = 3;  // layer 0 on the tensor core: xyz split hi/lo into a K = 16 operand, drained like KIND_HIDDEN
 struct Net {
   int32_t n_layers;
   int32_t l0_table;
@@ -221,7 +223,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
         const Net& N = P.nets[net];
         const int nl = N.n_layers;
         for (int l = 0; l < nl; l++) {
-          const int n_chunks = N.layers[l].n_chunks, k_stages = N.layers[l].k_stages;
+          const int n_chunks = N.layers[l].n_chunks, k_stages = N.layers[l].k_stages, k_steps = N.layers[l].k_steps;
           const uint32_t idesc = F16 ? ptx::umma_idesc_f16(256, (uint32_t)N.layers[l].mma_n) : ptx::umma_idesc_bf16(256, (uint32_t)N.layers[l].mma_n);
           const uint32_t tile16 = (uint32_t)N.layers[l].tile_bytes >> 4;
           const int src = l & 1;
@@ -234,6 +236,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             auto issue_stage = [&](uint32_t st, int sidx) {
               const uint64_t bd = b_desc0 + (uint64_t)(st * (STAGE_BYTES >> 4));
               if (debug & 2) return;
+              if (k_steps == 1) {  // layer 0: K = 16 operand in the first 32 B of the shared-memory rows
+                ptx::mma2_f16_ss(d_tmem, a_desc0, bd, idesc, 0u);
+                return;
+              }
               if (src == 0) {
                 const uint64_t ad = a_desc0 + (uint64_t)(sidx * 2 * (A_CHUNK_BYTES >> 4));
 #pragma unroll
@@ -322,38 +328,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       for (int net = 0; net < 2; net++) {
         if (!((P.net_mask >> net) & 1)) continue;
         const Net& N = P.nets[net];
-        // ---- layer 0 on CUDA cores: K = 3 after folding the latent into table.w; writes the shared-memory
-        // activations (free: their last readers, the MMAs of the previous even layer, completed before the
-        // accumulator barrier this thread passed last)
+        // ---- layer 0 goes to the tensor core as well: after folding the latent into the per-shape constant c it
+        // is c + W_xyz . (x, y, z), K = 3.  The point is split hi + lo into 16-bit pieces and multiplied against
+        // [W_hi | W_hi | W_lo] (K = 16 operand [p_hi | p_lo | p_hi | 0], error ~2^-17 of |W p|, far below the
+        // rounding of the activation it produces); c is the layer's bias.  The operand goes into the first 32 B of
+        // this point's shared-memory row (free: the last readers of the shared-memory activations, the MMAs of the
+        // previous layer that read them, completed before the accumulator barrier this thread passed last).
         const long long t_l0 = tick();
-        tc::epi_bar();  // everybody is past the previous use of sTab / sBias
+        tc::epi_bar();  // everybody is past the previous use of sBias
         {
           const float4* t = P.tables + N.l0_table * 512;
-          sTab[et] = __ldg(t + et);
-          sTab[et + 256] = __ldg(t + et + 256);
-          if (N.layers[0].kind == KIND_HIDDEN)
-            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] =
-                __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[0].bias_off) + et);
+          reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = make_float2(__ldg(&t[2 * et].w), __ldg(&t[2 * et + 1].w));
         }
-        tc::epi_bar();
-#pragma unroll 1
-        for (int j = 0; j < 4; j++) {
-          const int c = 2 * j + h;
+        if (h == 0) {
+          float hi[3], lo[3];
+          const float p3[3] = {x, y, z};
 #pragma unroll
-          for (int gq = 0; gq < 8; gq++) {
-            float v[8];
-#pragma unroll
-            for (int f = 0; f < 8; f++) {
-              const float4 t = sTab[c * 64 + gq * 8 + f];
-              v[f] = tc::leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
-            }
-            tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_op16x2<F16>(v[0], v[1]),
-                             ptx::pack_op16x2<F16>(v[2], v[3]), ptx::pack_op16x2<F16>(v[4], v[5]), ptx::pack_op16x2<F16>(v[6], v[7]));
+          for (int i = 0; i < 3; i++) {
+            hi[i] = ptx::round_op16<F16>(p3[i]);
+            lo[i] = p3[i] - hi[i];
           }
-          ptx::fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * j);
+          const float k[16] = {hi[0], hi[1], hi[2], lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) w[i] = ptx::pack_op16x2<F16>(k[2 * i], k[2 * i + 1]);
+          tc::st_shared_v4(a_row + ((0 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+          tc::st_shared_v4(a_row + ((1 ^ sw) << 4), w[4], w[5], w[6], w[7]);
         }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0);  // A_READY(shared memory, K range 0)
         w2 += tick() - t_l0;
 
         for (int l = 0; l < N.n_layers; l++) {
@@ -457,7 +461,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
           if (L.kind == KIND_HIDDEN_XYZ) {
             if (dsti) for (int j = 0; j < L.n_chunks; j++) drain(I1{}, I1{}, j);
             else for (int j = 0; j < L.n_chunks; j++) drain(I1{}, I0{}, j);
-          } else {
+          } else {  // KIND_HIDDEN and KIND_L0TC: bias + LeakyReLU
             if (dsti) for (int j = 0; j < L.n_chunks; j++) drain(I0{}, I1{}, j);
             else for (int j = 0; j < L.n_chunks; j++) drain(I0{}, I0{}, j);
           }

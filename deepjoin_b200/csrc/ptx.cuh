@@ -3,6 +3,8 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 namespace dj {
 namespace ptx {
@@ -359,6 +361,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
+// x rounded to the operand type, back in fp32 (for hi/lo operand splits)
+template <int F16>
+__device__ __forceinline__ float round_op16(float x) {
+  if (F16) return __half2float(__float2half_rn(x));
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
 template <>
 __device__ __forceinline__ uint32_t pack_op16x2<0>(float lo, float hi) { return pack_bf16x2(lo, hi); }
 template <>
