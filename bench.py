@@ -360,7 +360,7 @@ def main():
                        "grid_query_ms": q_ms, "marching_cubes_ms": mc_ms, "vertices": nv, "faces": nf,
                        "precision": args.precision},
             "e2e": {"value": world * npts * args.steps / (e2e_ms * 1e-3), "unit": "queries/s",
-                    "h2d_bytes_per_step": int(code.numel() * 4), "d2h_bytes_per_step": int(mesh.vertices.nbytes + len(mesh.faces) * 12),
+                    "h2d_bytes_per_step": int(code.numel() * 4), "d2h_bytes_per_step": int(mesh.vertices.nbytes + mesh.faces.nbytes),
                     "ms_per_step": e2e_ms / args.steps, "api": "deepjoin_b200.core.reconstruct.create_mesh"},
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,

@@ -52,6 +52,7 @@ SIGNATURES = {
     "dj_create_mesh_count": (c_i, [c_p, c_p, c_p, c_i, c_i, c_i, c_d, c_i, c_i, c_i, c_d, c_i, c_i,
                                    ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)]),
     "dj_create_mesh_fetch": (c_i, [c_p, c_p, c_p]),
+    "dj_create_mesh_fetch64": (c_i, [c_p, c_p, c_p, c_p]),
     "dj_mesh_merge_vertices": (c_i, [c_p, c_p, c_i64, c_p, c_i64, ctypes.POINTER(c_i64), c_p]),
     "dj_nn_query": (c_i, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p]),
     "dj_debug_umma_probe": (c_i, [c_p, c_p, c_i, c_i, c_i, ctypes.c_uint32, ctypes.c_uint64, c_p]),

@@ -97,6 +97,7 @@ def decode_shape(vec, decoder, dims, use_net=1, batch_size=2 ** 16, padding=0.0,
 
 
 _mc_work = {}
+_PINNED_MESH_LIMIT = 1 << 28  # larger meshes go to pageable memory
 
 
 def _work_for(device_index):
@@ -167,14 +168,19 @@ def create_mesh(vec, decoder, use_net, sigmoid=True, level=0.5, gradient_directi
                                       int(bool(decoder._return_occ)), int(bool(sigmoid)), float(level),
                                       int(gradient_direction == "descent"), decoder._prec(),
                                       ctypes.byref(nv), ctypes.byref(nf)))
-    vertices = np.empty((nv.value, 3), dtype=np.float64)
-    faces = np.empty((nf.value, 3), dtype=np.int32)
-    _lib.check(L.dj_create_mesh_fetch(w.handle, vertices.ctypes.data, faces.ctypes.data))
+    # host arrays come from torch's pinned-memory pool (blocks are recycled when the mesh is dropped), so the
+    # device->host copy runs at link rate and lands directly in the arrays the mesh keeps: float64
+    # vertices, int64 faces as trimesh holds them (faces are widened on the device)
+    pin = (nv.value * 24 + nf.value * 24) <= _PINNED_MESH_LIMIT
+    vertices = torch.empty((nv.value, 3), dtype=torch.float64, pin_memory=pin).numpy()
+    faces = torch.empty((nf.value, 3), dtype=torch.int64, pin_memory=pin).numpy()
+    bad = ctypes.c_int(0)
+    _lib.check(L.dj_create_mesh_fetch64(w.handle, vertices.ctypes.data, faces.ctypes.data, ctypes.byref(bad)))
     # trimesh's process=True (:189): the duplicate-vertex merge already ran on the device
     # (csrc/mesh_merge.cuh); non-finite vertices cannot come out of marching cubes on a finite grid,
-    # the check keeps the contract anyway
+    # the device-side check keeps the contract anyway
     mesh = Mesh(vertices=vertices, faces=faces, process=False)
-    if len(vertices) and not np.isfinite(vertices).all():
+    if bad.value:
         mesh.remove_infinite_values()
         mesh.merge_vertices()
     if f_out is not None:

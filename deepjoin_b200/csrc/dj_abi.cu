@@ -992,7 +992,7 @@ extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int
 struct DjMcWork {
   int device = 0;
   mc::Dims D{};
-  DevBuf var, counts, offs, edge, misc, verts, faces, merge;
+  DevBuf var, counts, offs, edge, misc, verts, faces, merge, wide;
   double* v64 = nullptr;  // create_mesh: final float64 vertices on the device (inside verts / merge)
   int64_t nblocks = 0, nv = 0, nf = 0;
   int bpp = 0;  // blocks per cell layer (grid.x of the marching-cubes kernels; grid.y = cell layers)
@@ -1015,7 +1015,7 @@ extern "C" int dj_mc_create(int device, DjMcWork** out) {
 extern "C" int dj_mc_destroy(DjMcWork* w) {
   if (!w) return DJ_OK;
   DeviceGuard g(w->device);
-  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge}) b->release();
+  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge, &w->wide}) b->release();
   delete w;
   return DJ_OK;
 }
@@ -1236,6 +1236,39 @@ extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* fa
   cudaStream_t st = 0;
   DJ_CUDA(cudaMemcpyAsync(verts_host, w->v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaMemcpyAsync(faces_host, w->faces.as<int>(), (size_t)w->nf * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaStreamSynchronize(st));
+  return DJ_OK;
+}
+
+// faces widened to the int64 a trimesh.Trimesh holds, and a non-finite-vertex flag, both produced on the device so that the
+// host wrapper neither converts nor scans the arrays (core/reconstruct.py:189: Trimesh(vertices, faces))
+__global__ void mesh_widen_kernel(const int32_t* __restrict__ f32, int64_t* __restrict__ f64, int64_t nf3, const double* __restrict__ v,
+                                  int64_t nv3, int* __restrict__ flag) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nf3) f64[i] = (int64_t)f32[i];
+  bool bad = false;
+  if (i < nv3) bad = !isfinite(v[i]);
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+
+extern "C" int dj_create_mesh_fetch64(DjMcWork* w, double* verts_host, int64_t* faces_host, int* nonfinite) {
+  if (!w || !w->counted || !w->v64 || !verts_host || !faces_host || !nonfinite)
+    return fail(DJ_ERR_INVALID, "dj_create_mesh_fetch64: bad argument");
+  DeviceGuard g(w->device);
+  cudaStream_t st = 0;
+  const int64_t nf3 = w->nf * 3, nv3 = w->nv * 3;
+  DJ_CUDA(w->wide.reserve((size_t)nf3 * sizeof(int64_t) + 16));
+  int64_t* f64 = w->wide.as<int64_t>();
+  int* flag = reinterpret_cast<int*>(f64 + nf3);
+  DJ_CUDA(cudaMemsetAsync(flag, 0, sizeof(int), st));
+  const int64_t n = nf3 > nv3 ? nf3 : nv3;
+  if (n) {
+    mesh_widen_kernel<<<(unsigned)ceil_div(n, (int64_t)256), 256, 0, st>>>(w->faces.as<int>(), f64, nf3, w->v64, nv3, flag);
+    DJ_LAUNCHED();
+  }
+  DJ_CUDA(cudaMemcpyAsync(verts_host, w->v64, (size_t)nv3 * sizeof(double), cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaMemcpyAsync(faces_host, f64, (size_t)nf3 * sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+  DJ_CUDA(cudaMemcpyAsync(nonfinite, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaStreamSynchronize(st));
   return DJ_OK;
 }

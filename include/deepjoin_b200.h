@@ -186,6 +186,10 @@ int dj_create_mesh_count(DjPack* pack, DjMcWork* work, const float* code_host, i
                          double padding, int use_net, int return_occ, int apply_sigmoid, double level,
                          int descent, int precision, int64_t* n_verts, int64_t* n_faces);
 int dj_create_mesh_fetch(DjMcWork* work, double* verts_host, int32_t* faces_host);
+/* same, with faces widened on the device to the int64 a trimesh.Trimesh holds (core/reconstruct.py:189) and
+ * *nonfinite = 1 when any vertex coordinate is NaN/Inf (what Trimesh(process=True) would have removed);
+ * host buffers may be pinned (the Python wrapper takes them from torch's pinned-memory pool). */
+int dj_create_mesh_fetch64(DjMcWork* work, double* verts_host, int64_t* faces_host, int* nonfinite);
 
 /* replaces: the duplicate-vertex merge of trimesh.Trimesh(vertices, faces) (default process=True,
  * core/reconstruct.py:189): vertices whose coordinates agree after rounding to 8 decimals collapse onto
