@@ -39,7 +39,12 @@ def select_sample_indices(values, num_samples=None, uniform_ratio=0.5):
             raise NotImplementedError("multi-shape value columns")
         values = values[:, 0]
     rows = _uniform_ratio_rows(values.shape[0], uniform_ratio) if uniform_ratio is not None else np.arange(values.shape[0])
-    d = values[rows]
+    return rows[_fair_windows(values[rows], num_samples)]
+
+
+def _fair_windows(d, num_samples):
+    """core/data.py:46-73 for one value column: a contiguous window of the positive rows and one of the
+    non-positive rows (negatives drawn first), as positions into ``d``."""
     s = d.shape[0] if num_samples is None else num_samples
     pos_inds = np.where(d > 0)[0]
     neg_inds = np.where(d <= 0)[0]
@@ -60,7 +65,29 @@ def select_sample_indices(values, num_samples=None, uniform_ratio=0.5):
             pos_picked = np.random.choice(pos_inds, pos_num)
         except ValueError:
             raise errors.NoSamplesError
-    return rows[np.concatenate([pos_picked, neg_picked])]
+    return np.concatenate([pos_picked, neg_picked])
+
+
+def select_partial_sample_indices(values, mask, num_samples=None, uniform_ratio=0.5):
+    """Indices such that ``pts[idx], values[idx]`` equals the reference's
+    ``select_partial_samples(pts, values, mask, num_samples, uniform_ratio)`` (core/data.py:76-119):
+    ratio selection without shuffling, keep the rows where ``mask`` is set (np.intersect1d leaves them
+    in ascending row order), permute, then the fair windows."""
+    values = np.asarray(values)
+    if values.ndim == 2:
+        if values.shape[1] != 1:
+            raise NotImplementedError("multi-shape value columns")
+        values = values[:, 0]
+    rows = _uniform_ratio_rows(values.shape[0], uniform_ratio, randomize=False)
+    keep = np.intersect1d(rows, np.where(np.asarray(mask).reshape(-1))[0])
+    keep = keep[np.random.permutation(keep.shape[0])]
+    return keep[_fair_windows(values[keep], num_samples)]
+
+
+def select_partial_samples(pts, values, mask, num_samples=None, uniform_ratio=0.5):
+    """core/data.py:76-119 (one value column)."""
+    idx = select_partial_sample_indices(values, mask, num_samples, uniform_ratio)
+    return pts[idx, :], values[idx, :]
 
 
 def select_samples(pts, values, num_samples=None, uniform_ratio=0.5):

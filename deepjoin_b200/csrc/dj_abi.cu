@@ -37,8 +37,10 @@ struct DjPack {
   unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
   // fused forward+backward program of the latent step (latent_tc2.cuh)
   uint8_t* lat_stream[2] = {nullptr, nullptr};
+  uint8_t* lat_stream_h[2] = {nullptr, nullptr};  // forward tiles in IEEE half
   lat2::Layer lat_prog[lat2::MAX_PROG];
   int lat_n_prog = 0;
+  int lat_net1_lo = 0, lat_net1_hi = 0;  // program entries of the second net (forward + backward)
   bool lat_attr_set = false;
   int tc_kernel = 2;  // 2: CTA-pair kernel (default); 1: single-CTA kernel (env DEEPJOIN_B200_TC=1)
   // per-call shape constants + device error word
@@ -66,8 +68,10 @@ static void free_pack(DjPack* p) {
       if (p->stream2h[i][r]) cudaFree(p->stream2h[i][r]);
   }
   if (p->bias_dev) cudaFree(p->bias_dev);
-  for (int r = 0; r < 2; r++)
+  for (int r = 0; r < 2; r++) {
     if (p->lat_stream[r]) cudaFree(p->lat_stream[r]);
+    if (p->lat_stream_h[r]) cudaFree(p->lat_stream_h[r]);
+  }
   if (p->tables) cudaFree(p->tables);
   if (p->err) cudaFree(p->err);
   if (p->prof) cudaFree(p->prof);
@@ -355,7 +359,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     const int nlf = d->f_layers, nlh = d->h_layers;
     if ((nlf - 1) + (nlh - 1) + 2 > lat2::MASK_LAYERS + 2 || nlf - 1 + nlh - 1 != lat2::MASK_LAYERS)
       return bail(fail(DJ_ERR_UNSUPPORTED, "latent step: %d + %d hidden activations (built for %d)", nlf - 1, nlh - 1, lat2::MASK_LAYERS));
-    std::vector<uint8_t> blob[2];
+    std::vector<uint8_t> blob[2], blobh[2];  // blobh: forward tiles in IEEE half (DJ_PREC_FP16), backward tiles bf16 as in blob
     int np = 0;
     auto add = [&](int kind, int src, int dst, int n_chunks, int k_stages, int k_steps, int mma_n, int mask_layer, int slot,
                    int bias_off, int after) -> lat2::Layer& {
@@ -377,7 +381,9 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
             for (int kc = 0; kc < (T.k_steps == 1 ? 1 : 2); kc++) {
               const size_t o = blob[r].size();
               blob[r].resize(o + T.tile_bytes);
-              tile_fn(j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blob[r].data() + o);
+              blobh[r].resize(o + T.tile_bytes);
+              tile_fn(j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blob[r].data() + o, false);
+              tile_fn(j * T.mma_n + r * rows, (2 * st + kc) * 64, rows, blobh[r].data() + o, true);
             }
     };
     int buf = 0;  // where the current activations live: 0 shared memory, 1 tensor memory
@@ -388,6 +394,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
       const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
       const tc2::Net& N2 = p->nets2[net];
+      if (net == 1) p->lat_net1_lo = np;
       add(lat2::K_L0, 2, 0, 0, 0, 0, 0, mask++, net == 0 ? 0 : 2, 0, 0);
       buf = 0;
       for (int l = 1; l < nl; l++) {
@@ -398,7 +405,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
         const int kind = head ? (net == 0 ? lat2::K_HEAD_F : lat2::K_HEAD_H) : (reinj ? lat2::K_FWD_XYZ : lat2::K_FWD);
         lat2::Layer& T = add(kind, buf, head ? 2 : 1 - buf, F.n_chunks, F.k_stages, 8, F.mma_n, head ? 0 : mask, reinj ? 1 : 0,
                              F.bias_off, 0);
-        emit(T, [&](int n0, int k0, int rows, uint8_t* dst) { pack_tile(W[l], ins[l], outs[l], k_real, n0, k0, rows, dst); });
+        emit(T, [&](int n0, int k0, int rows, uint8_t* dst, bool f16) { pack_tile(W[l], ins[l], outs[l], k_real, n0, k0, rows, dst, f16); });
         if (!head) { mask++; buf = 1 - buf; }
       }
     }
@@ -409,10 +416,11 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
       const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
       const int mask0 = net == 0 ? 0 : nlf - 1;  // mask layer of this net's layer-0 output
+      if (net == 0) p->lat_net1_hi = np;
       // head: K = 16 operand in shared memory -> gradient of the last hidden activation, into tensor memory
       {
         lat2::Layer& T = add(lat2::K_BWD, 0, 1, 4, 1, 1, 128, mask0 + nl - 2, 0, 0, 0);
-        emit(T, [&](int n0, int, int rows, uint8_t* dst) { pack_tile_head_T(W[nl - 1], ins[nl - 1], n0, rows, dst); });
+        emit(T, [&](int n0, int, int rows, uint8_t* dst, bool) { pack_tile_head_T(W[nl - 1], ins[nl - 1], n0, rows, dst); });
       }
       buf = 1;
       for (int l = nl - 2; l >= 1; l--) {
@@ -427,7 +435,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
         const int slot = last ? (net == 0 ? 0 : 2) : 1;
         lat2::Layer& T = add(kind, buf, last ? 2 : 1 - buf, n_chunks, k_stages, 8, 128, mask0 + l - 1, slot, 0,
                              (last && net == 1) ? 1 : 0);
-        emit(T, [&](int n0, int k0, int rows, uint8_t* dst) { pack_tile_T(W[l], ins[l], out_real, in_real, n0, k0, rows, dst); });
+        emit(T, [&](int n0, int k0, int rows, uint8_t* dst, bool) { pack_tile_T(W[l], ins[l], out_real, in_real, n0, k0, rows, dst); });
         buf = 1 - buf;
       }
     }
@@ -435,6 +443,8 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     for (int r = 0; r < 2; r++) {
       DJ_TRY(cudaMalloc((void**)&p->lat_stream[r], blob[r].size()));
       DJ_TRY(cudaMemcpy(p->lat_stream[r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
+      DJ_TRY(cudaMalloc((void**)&p->lat_stream_h[r], blobh[r].size()));
+      DJ_TRY(cudaMemcpy(p->lat_stream_h[r], blobh[r].data(), blobh[r].size(), cudaMemcpyHostToDevice));
     }
   }
   DJ_TRY(upload(bias_host.data(), bias_host.size(), &p->bias_dev));
@@ -770,7 +780,7 @@ static int latent_fwd_bwd(DjPack* p, const float* code_dev, const float* xyz, co
   if ((rc = launch_fold(p, code_dev, st))) return rc;
   if ((rc = fp32_forward(p, xyz, n, 3, W.fH.data(), W.hH.data(), W.yC, W.yT, st))) return rc;
   DJ_CUDA(cudaMemsetAsync(W.colsum, 0, (3 * 512 + 8) * sizeof(float), st));  // colsum + loss_acc are contiguous
-  simt::LossCfg LC{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, slope, 1.0f / (float)n};
+  simt::LossCfg LC{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, slope, 1.0f / (float)n, cfg->loss_kind};
   simt::loss_grad_kernel<<<ceil_div(n, 256), 256, 0, st>>>(LC, W.yC, W.yT, 8, sdf, nrm, W.dyC, W.dyT, W.loss_acc, n);
   DJ_LAUNCHED();
   auto colsum = [&](const float* G, int slot) -> int {
@@ -860,23 +870,28 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
   memset(&P, 0, sizeof P);
   memcpy(P.prog, p->lat_prog, sizeof(lat2::Layer) * p->lat_n_prog);
   P.n_prog = p->lat_n_prog;
-  P.stream[0] = p->lat_stream[0];
-  P.stream[1] = p->lat_stream[1];
+  const bool half_fwd = cfg->precision == DJ_PREC_FP16;  // forward in IEEE half (8x finer than bf16: the loss gates follow
+                                                         // the fp32 forward far more often); backward always bf16 (range)
+  P.stream[0] = half_fwd ? p->lat_stream_h[0] : p->lat_stream[0];
+  P.stream[1] = half_fwd ? p->lat_stream_h[1] : p->lat_stream[1];
   P.bias = p->bias_dev;
   P.tables = p->tables;
   P.xyz = W.ptrs; P.sdf = W.ptrs + S; P.nrm = W.ptrs + 2 * S;
   P.idx = idx; P.idx_stride = idx_stride;
   P.n = n;
   P.n_shapes = S; P.tiles_per_shape = (int32_t)tps;
-  P.loss = simt::LossCfg{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, p->desc.slope, 1.0f / (float)n};
+  P.loss = simt::LossCfg{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, p->desc.slope, 1.0f / (float)n, cfg->loss_kind};
+  if (cfg->loss_kind == DJ_LOSS_DEEPSDF) { P.skip_lo = p->lat_net1_lo; P.skip_hi = p->lat_net1_hi; }
   P.masks = p->ws_mask.as<unsigned long long>();
   P.acc = W.acc;
   P.err = p->err;
   if (!p->lat_attr_set) {
-    DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
+    DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
+    DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
     p->lat_attr_set = true;
   }
-  lat2::latent_tc2_kernel<<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
+  if (half_fwd) lat2::latent_tc2_kernel<true><<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
+  else lat2::latent_tc2_kernel<false><<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
   DJ_LAUNCHED();
   simt::GradFinishParams GP;
   for (int i = 0; i < 3; i++) { GP.src[i] = p->fold.src[i]; GP.colsum[i] = W.acc + i * 512; }
@@ -894,6 +909,8 @@ static int check_latent_cfg(DjPack* p, const DjLatentCfg* cfg) {
   if (cfg->precision != DJ_PREC_FP32 && cfg->precision != DJ_PREC_BF16 && cfg->precision != DJ_PREC_FP16)
     return fail(DJ_ERR_INVALID, "latent gradient: unknown precision %d", cfg->precision);
   if (p->L + p->Lb > 256) return fail(DJ_ERR_UNSUPPORTED, "code length > 256");
+  if (cfg->loss_kind != DJ_LOSS_DEEPJOIN && cfg->loss_kind != DJ_LOSS_DEEPSDF)
+    return fail(DJ_ERR_INVALID, "latent gradient: unknown loss_kind %d", cfg->loss_kind);
   return DJ_OK;
 }
 
@@ -941,7 +958,7 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
   const int C = p->L + p->Lb;
   const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
   const int64_t log_rows = (cfg->num_iterations + log_every - 1) / log_every;
-  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations};
+  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations, cfg->loss_kind == DJ_LOSS_DEEPSDF ? 1 : 0};
   if (cfg->precision != DJ_PREC_FP32) {
     // all shapes in one launch per iteration; the kernel gathers every shape's mini-batch rows itself
     LatTcWs T;

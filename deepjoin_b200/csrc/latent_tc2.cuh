@@ -75,6 +75,7 @@ struct Layer {
 struct Params {
   Layer prog[MAX_PROG];
   int32_t n_prog, debug;
+  int32_t skip_lo, skip_hi;  // program entries [skip_lo, skip_hi) are not executed (single-net packs: the second net)
   const uint8_t* stream[2];  // per cluster rank, stages in program order
   const float* bias;
   const float4* tables;      // [3][512] per-shape constants (fold_kernel)
@@ -109,6 +110,8 @@ __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
   return v[0];
 }
 
+// F16: the FORWARD layers (activations + their weight tiles) are IEEE half instead of bf16; gradients stay bf16
+template <bool F16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_tc2_kernel(const __grid_constant__ Params P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -159,6 +162,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
       for (int l = 0; l < P.n_prog; l++) {
         const int ns = P.prog[l].n_chunks * P.prog[l].k_stages;
         const uint32_t bytes = (uint32_t)P.prog[l].stage_bytes;
+        if (l >= P.skip_lo && l < P.skip_hi) { src += (size_t)ns * bytes; continue; }
         for (int s = 0; s < ns; s++) {
           ptx::mbar_wait(W_EMPTY(stage), phase ^ 1, P.err, 0x100 | stage);
           if (ptx::elect_one()) {
@@ -174,7 +178,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
   } else if (warp == 1 && rank != 0) {
     // ===================== peer: relay "my half of the stage has landed" to the leader =====================
     int per_pass = 0;
-    for (int l = 0; l < P.n_prog; l++) per_pass += P.prog[l].n_chunks * P.prog[l].k_stages;
+    for (int l = 0; l < P.n_prog; l++)
+      if (l < P.skip_lo || l >= P.skip_hi) per_pass += P.prog[l].n_chunks * P.prog[l].k_stages;
     const uint32_t lead_full0 = ptx::mapa(W_FULL(0), 0);
     uint32_t stage = 0, phase = 0;
     for (int64_t i = 0; i < iters * per_pass; i++) {
@@ -193,8 +198,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
     for (int64_t it = 0; it < iters; it++) {
       for (int l = 0; l < P.n_prog; l++) {
         const int n_chunks = P.prog[l].n_chunks, k_stages = P.prog[l].k_stages, k_steps = P.prog[l].k_steps;
-        if (n_chunks == 0) continue;  // epilogue-only entry
-        const uint32_t idesc = ptx::umma_idesc_bf16(256, (uint32_t)P.prog[l].mma_n);
+        if (n_chunks == 0 || (l >= P.skip_lo && l < P.skip_hi)) continue;  // epilogue-only / skipped entry
+        const bool fwd_l = P.prog[l].kind <= K_HEAD_H;
+        const uint32_t idesc = (F16 && fwd_l) ? ptx::umma_idesc_f16(256, (uint32_t)P.prog[l].mma_n) : ptx::umma_idesc_bf16(256, (uint32_t)P.prog[l].mma_n);
         const uint32_t tile16 = (uint32_t)P.prog[l].tile_bytes >> 4;
         const int src = P.prog[l].src;
         for (int j = 0; j < n_chunks; j++) {
@@ -326,6 +332,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
 
       for (int l = 0; l < P.n_prog; l++) {
         const Layer L = P.prog[l];
+        if (l >= P.skip_lo && l < P.skip_hi) continue;
         if (L.kind == K_L0) {
           // ---- layer 0 on CUDA cores (K = 3 after folding the latent into table.w) -> shared-memory activations
           tc::epi_bar();
@@ -348,8 +355,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
                 v[f] = tc::leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
                 m |= (unsigned long long)(v[f] > 0.f) << (gq * 8 + f);
               }
-              tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_bf16x2(v[0], v[1]),
-                               ptx::pack_bf16x2(v[2], v[3]), ptx::pack_bf16x2(v[4], v[5]), ptx::pack_bf16x2(v[6], v[7]));
+              tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_op16x2<F16>(v[0], v[1]),
+                               ptx::pack_op16x2<F16>(v[2], v[3]), ptx::pack_op16x2<F16>(v[4], v[5]), ptx::pack_op16x2<F16>(v[6], v[7]));
             }
             mrow[(size_t)(L.mask_layer * 4 + j) * 256] = m;
             ptx::fence_proxy_async_smem();
@@ -379,7 +386,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
               else yt[i] = tc::leaky(v, slope);  // decoder :259-270
             }
           }
-          if (L.kind == K_HEAD_H) {
+          // the loss follows the last head: the hnet's, or the fnet's own when the second net is skipped
+          if (L.kind == K_HEAD_H || P.skip_hi > P.skip_lo) {
             // ---- loss and d loss / d head pre-activations of this sample (reconstruct.py:166-192)
             float gt[5] = {0, 0, 0, 0, 0};
             float l3[3] = {0.f, 0.f, 0.f};
@@ -393,8 +401,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
               }
               if (lane < 3) atomicAdd(loss_acc + lane, lane == 0 ? l3[0] : (lane == 1 ? l3[1] : l3[2]));
             }
-            // the hnet head read the shared-memory activations; its MMAs are complete (accumulator barrier above)
-            write_head_operand(gt);
+            // the last readers of the shared-memory activations (the hnet head, or the fnet's last hidden layer)
+            // are complete: every accumulator barrier up to this head has been passed
+            if (L.kind == K_HEAD_H) write_head_operand(gt);
+            else write_head_operand(gc);
           }
           continue;
         }
@@ -470,7 +480,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
             }
             if (KIND != K_SUM) {
 #pragma unroll
-              for (int f = 0; f < 4; f++) pk[gq * 4 + f] = ptx::pack_bf16x2(v[2 * f], v[2 * f + 1]);
+              for (int f = 0; f < 4; f++)
+                pk[gq * 4 + f] = (KIND == K_FWD || KIND == K_FWD_XYZ) ? ptx::pack_op16x2<F16>(v[2 * f], v[2 * f + 1]) : ptx::pack_bf16x2(v[2 * f], v[2 * f + 1]);
               if (DST == 0)
                 tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), pk[gq * 4], pk[gq * 4 + 1], pk[gq * 4 + 2],
                                  pk[gq * 4 + 3]);

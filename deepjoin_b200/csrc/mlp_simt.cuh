@@ -186,6 +186,7 @@ __global__ void heads_kernel(HeadCfg H, const float* __restrict__ yC, const floa
 struct LossCfg {
   float lambda1, lambda3, clamp_dist, slope;
   float inv_n;
+  int kind;  // DJ_LOSS_DEEPJOIN | DJ_LOSS_DEEPSDF
 };
 
 // Loss of ONE sample and its gradient wrt the 2 x 5 head pre-activations (reconstruct.py:166-192):
@@ -193,6 +194,19 @@ struct LossCfg {
 // gc / gt: d loss / d (head pre-activations); l3 += (sdf, occ, normal) loss terms of this sample.
 __device__ __forceinline__ void loss_row(const LossCfg& L, const float (&yc)[5], const float (&yt)[5], float s,
                                          const float (&n_gt)[3], float (&gc)[5], float (&gt)[5], float (&l3)[3]) {
+  if (L.kind == 1) {
+    // baseline DeepSDF objective (reconstruct_deepsdf.py:109-127): L1 between the clamped prediction
+    // tanh(y0) (decoder_deepsdf.py:103-104) and the clamped target; only the first head row exists
+    const float pred = tanhf(yc[0]);
+    const float diff = fminf(fmaxf(pred, -L.clamp_dist), L.clamp_dist) - fminf(fmaxf(s, -L.clamp_dist), L.clamp_dist);
+    l3[0] += L.inv_n * fabsf(diff);
+    const float sg = (diff > 0.f) ? 1.f : (diff < 0.f ? -1.f : 0.f);
+    const bool pass = (pred >= -L.clamp_dist) && (pred <= L.clamp_dist);
+#pragma unroll
+    for (int i = 0; i < 5; i++) { gc[i] = 0.f; gt[i] = 0.f; }
+    gc[0] = pass ? L.inv_n * sg * (1.f - pred * pred) : 0.f;
+    return;
+  }
   const float c_sdf = tanhf(yc[0]), t_sdf = tanhf(yt[0]);
   const float sc = sigmoidf_(yc[1]), st = sigmoidf_(yt[1]);
   float cn[3], tn[3];
@@ -352,6 +366,7 @@ __global__ void loss_finish_kernel(const float* __restrict__ loss_acc, float* __
 struct AdamCfg {
   float lr, beta1, beta2, eps;
   int num_iterations;
+  int mag_after_step;
 };
 // blockIdx.x = shape of a batch (code / m / v + x*code_stride, grad + x*grad_stride, terms + x*terms_stride,
 // log_row + x*log_stride)
@@ -369,30 +384,38 @@ __global__ void adam_kernel(AdamCfg A, int e, float* __restrict__ code, float* _
   __shared__ float sq[2];
   if (i < 2) sq[i] = 0.f;
   __syncthreads();
-  if (log_row && i < n) atomicAdd(&sq[i < L ? 0 : 1], code[i] * code[i]);  // |z|, |z_b| BEFORE the step (:210-211)
+  float c_old = 0.f, c_new = 0.f;
+  if (i < n) {
+    const int half = A.num_iterations / 2;
+    float lr = A.lr;
+    if (half > 0) {
+      const int k = e / half;
+      for (int q = 0; q < k; q++) lr *= 0.1f;
+    }
+    const float g = grad[i];
+    const float mi = A.beta1 * m[i] + (1.f - A.beta1) * g;
+    const float vi = A.beta2 * v[i] + (1.f - A.beta2) * g * g;
+    m[i] = mi;
+    v[i] = vi;
+    const float step = (float)(e + 1);
+    const float bc1 = 1.f - powf(A.beta1, step), bc2 = 1.f - powf(A.beta2, step);
+    const float denom = sqrtf(vi) / sqrtf(bc2) + A.eps;
+    c_old = code[i];
+    c_new = c_old - (lr / bc1) * mi / denom;
+    code[i] = c_new;
+  }
+  if (!log_row) return;
+  // |z|, |z_b|: DeepJoin's loop logs them BEFORE the step (reconstruct.py:210-211), the DeepSDF baseline's AFTER
+  // optimizer.step() (reconstruct_deepsdf.py:134-141)
+  const float c = A.mag_after_step ? c_new : c_old;
+  if (i < n) atomicAdd(&sq[i < L ? 0 : 1], c * c);
   __syncthreads();
-  if (log_row && i == 0) {
+  if (i == 0) {
     log_row[0] = (float)e;
     for (int k = 0; k < 5; k++) log_row[1 + k] = terms[k];
     log_row[6] = sqrtf(sq[0]);
     log_row[7] = sqrtf(sq[1]);
   }
-  if (i >= n) return;
-  const int half = A.num_iterations / 2;
-  float lr = A.lr;
-  if (half > 0) {
-    const int k = e / half;
-    for (int q = 0; q < k; q++) lr *= 0.1f;
-  }
-  const float g = grad[i];
-  const float mi = A.beta1 * m[i] + (1.f - A.beta1) * g;
-  const float vi = A.beta2 * v[i] + (1.f - A.beta2) * g * g;
-  m[i] = mi;
-  v[i] = vi;
-  const float step = (float)(e + 1);
-  const float bc1 = 1.f - powf(A.beta1, step), bc2 = 1.f - powf(A.beta2, step);
-  const float denom = sqrtf(vi) / sqrtf(bc2) + A.eps;
-  code[i] -= (lr / bc1) * mi / denom;
 }
 
 // batch gather from the resident sample pool

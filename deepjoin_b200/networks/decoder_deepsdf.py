@@ -55,6 +55,10 @@ class Decoder(nn.Module):
             wn = weight_norm and (layer in (norm_layers or ()))
             setattr(self, "lin%d" % layer, (_WNLinear if wn else _Linear)(dims[layer], out_dim))
         self.precision = os.environ.get("DEEPJOIN_B200_PRECISION", "bf16")
+        # latent optimisation (reconstruct_deepsdf.reconstruct): the baseline's objective is a sign-gated L1, so a
+        # forward rounding error flips whole per-sample gradients; IEEE-half forward operands (8x finer than bf16)
+        # keep the tensor-core gradient within ~1e-2 of fp32 even at small batches
+        self.latent_precision = None  # None: "fp16" when precision is "bf16", else precision (latent_prec())
         self._pack = None
         self._pack_key = None
 
@@ -87,6 +91,9 @@ class Decoder(nn.Module):
         if p not in _lib.PREC:
             raise ValueError("precision must be one of %s" % sorted(_lib.PREC))
         return _lib.PREC[p]
+
+    def latent_prec(self):
+        return self.latent_precision or ("fp16" if self.precision == "bf16" else self.precision)
 
     def _check_eval(self):
         if self.training:

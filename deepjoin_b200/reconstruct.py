@@ -46,7 +46,7 @@ def init_code(latent_size, break_latent_size, stat):
 
 
 def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, lambda1, lambda3, clamp_dist,
-                  l2reg=True, code_reg_lambda=1e-4, log_every=10, precision="fp32"):
+                  l2reg=True, code_reg_lambda=1e-4, log_every=10, precision="fp32", loss_kind=0):
     """Device loop.  pool_* CUDA f32 tensors ([M,3], [M], [M,3]); schedule CUDA int32
     [iterations, num_samples].  Returns (log [ceil(it/log_every), 8] CUDA, code [1, L+Lb] CUDA)."""
     dev = pool_xyz.device
@@ -54,7 +54,7 @@ def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, la
     iters, ns = int(schedule.shape[0]), int(schedule.shape[1])
     cfg = _lib.LatentCfg(iters, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
                          float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, int(log_every),
-                         _lib.PREC[precision])
+                         _lib.PREC[precision], int(loss_kind))
     code = code0.detach().reshape(-1).to(device=dev, dtype=torch.float32).clone().contiguous()
     m = torch.zeros_like(code)
     v = torch.zeros_like(code)
@@ -102,12 +102,13 @@ def optimize_codes(decoder, codes0, pools, schedules, lr, lambda1, lambda3, clam
 
 
 def latent_grad(decoder, code, xyz, sdf, nrm, lambda1=1.0, lambda3=1.0, clamp_dist=0.1, l2reg=True,
-                code_reg_lambda=1e-4, precision="fp32"):
+                code_reg_lambda=1e-4, precision="fp32", loss_kind=0):
     """One forward+backward: (dL/dcode [L+Lb], loss terms [5] = loss, sdf, occ, norm, reg)."""
     dev = xyz.device
     pack = decoder.pack(dev)
     cfg = _lib.LatentCfg(1, int(xyz.shape[0]), 0.0, float(lambda1), float(lambda3), float(clamp_dist),
-                         float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, 10, _lib.PREC[precision])
+                         float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, 10, _lib.PREC[precision],
+                         int(loss_kind))
     code = code.detach().reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
     grad = torch.empty_like(code)
     terms = torch.empty(5, device=dev, dtype=torch.float32)

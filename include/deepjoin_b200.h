@@ -118,7 +118,13 @@ typedef struct DjLatentCfg {
   float   beta1, beta2, eps;/* torch.optim.Adam defaults .9/.999/1e-8 (:58)          */
   int32_t log_every;        /* 10 (:203)                                             */
   int32_t precision;
+  int32_t loss_kind;        /* DJ_LOSS_DEEPJOIN (0) | DJ_LOSS_DEEPSDF (1)            */
 } DjLatentCfg;
+/* DJ_LOSS_DEEPSDF: the baseline's objective (reconstruct_deepsdf.py:109-134) on the single-net pack a
+ * DeepSDF decoder builds: mean |clamp(tanh(y0), +-d) - clamp(sdf, +-d)| + reg; lambda1 / lambda3 and the
+ * normals are ignored, the second net is neither evaluated nor differentiated. */
+#define DJ_LOSS_DEEPJOIN 0
+#define DJ_LOSS_DEEPSDF 1
 
 /* One forward+backward: loss terms [5] = (loss, sdf, occ, norm, reg) and dL/dcode [L+Lb].
  * xyz_dev [n,3], sdf_dev [n], nrm_dev [n,3] f32. */

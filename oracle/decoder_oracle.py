@@ -292,3 +292,54 @@ def deepsdf_forward(sd, latent, pts, dtype=torch.float32, latent_in=4):
         if l < n_layers - 1:
             x = torch.relu(x)
     return torch.tanh(x)
+
+
+def select_partial_samples(pts, values, mask, num_samples=None, uniform_ratio=0.5):
+    """core/data.py:76-119: ratio selection without the shuffle, keep the rows ``mask`` marks (np.intersect1d
+    returns them in ascending row order), shuffle, then the fair windows of select_samples."""
+    ids = np.arange(pts.shape[0], dtype=np.float64).reshape(-1, 1)
+    pts_i, values = select_uniform_ratio_samples(np.hstack((ids, pts)), values, uniform_ratio, randomize=False)
+    keep = np.nonzero(np.isin(pts_i[:, 0], np.where(mask)[0]))[0]
+    keep = keep[np.argsort(pts_i[keep, 0], kind="stable")]
+    pts, values = pts_i[keep, 1:], values[keep, :]
+    perm = np.random.permutation(pts.shape[0])
+    return select_samples(pts[perm], values[perm], num_samples, uniform_ratio=None)
+
+
+def deepsdf_loss_terms(sd, latent, xyz, sdf_gt, clamp_dist=0.1, code_reg_lambda=1e-4, l2reg=True, dtype=torch.float32):
+    """reconstruct_deepsdf.py:112-134: L1 between the clamped prediction and the clamped target (+ regulariser).
+    Returns (loss, data_loss, reg_loss)."""
+    pred = torch.clamp(deepsdf_forward(sd, latent, xyz, dtype), -clamp_dist, clamp_dist)
+    gt = torch.clamp(sdf_gt.to(dtype).reshape(-1, 1), -clamp_dist, clamp_dist)
+    data = torch.nn.functional.l1_loss(pred, gt)
+    reg = code_reg_lambda * torch.mean(latent.pow(2)) if l2reg else torch.zeros((), dtype=dtype)
+    return data + reg, data, reg
+
+
+def deepsdf_latent_grad(sd, latent, xyz, sdf_gt, **kw):
+    latent = latent.detach().clone().reshape(1, -1).requires_grad_(True)
+    terms = deepsdf_loss_terms(sd, latent, xyz, sdf_gt, **kw)
+    terms[0].backward()
+    return latent.grad.detach().reshape(-1), [float(t.detach()) for t in terms]
+
+
+def deepsdf_adam_loop(sd, latent0, batches, num_iterations, lr=5e-3, betas=(0.9, 0.999), eps=1e-8, log_every=10, **kw):
+    """reconstruct_deepsdf.py:46,98-152 with an injected sample schedule ``batches(e) -> (xyz, sdf)``."""
+    code = latent0.detach().clone().reshape(-1)
+    m = torch.zeros_like(code)
+    v = torch.zeros_like(code)
+    log = {k: [] for k in ("epoch", "data_loss", "reg_loss", "mag")}
+    for e in range(num_iterations):
+        xyz, sdf = batches(e)
+        g, t = deepsdf_latent_grad(sd, code, xyz, sdf, **kw)
+        step = e + 1
+        m = betas[0] * m + (1 - betas[0]) * g
+        v = betas[1] * v + (1 - betas[1]) * g * g
+        step_size = lr_at(e, lr, num_iterations) / (1 - betas[0] ** step)
+        code = code - step_size * m / (v.sqrt() / math.sqrt(1 - betas[1] ** step) + eps)
+        if e % log_every == 0:  # the reference logs AFTER optimizer.step(): the norm is the updated latent's (:136-141)
+            log["epoch"].append(e)
+            log["data_loss"].append(t[1])
+            log["reg_loss"].append(t[2])
+            log["mag"].append(float(code.norm()))
+    return log, code.reshape(1, -1)

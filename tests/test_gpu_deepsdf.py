@@ -57,3 +57,99 @@ def test_create_mesh_and_values2mesh():
     assert np.array_equal(again.faces, want.faces) and np.allclose(again.vertices, want.vertices, rtol=0, atol=1e-12)
     sdf = U.decode_sdf(dec, latent.reshape(1, -1), pts[:100])
     assert np.abs(sdf.cpu().numpy().reshape(-1) - ref.reshape(-1)[:100]).max() < 3e-4
+
+
+# ---------------------------------------------------------------- latent optimisation (reconstruct_deepsdf.py:17-154)
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16"])
+def test_latent_gradient_matches_reference_autograd(kind, precision):
+    """d loss / d latent of the baseline objective against the reference's own autograd (golden grad0)."""
+    from deepjoin_b200 import reconstruct as R
+    g = np.load(os.path.join(G, "deepsdf_reconstruct.npz"))
+    dec = _decoder(0, kind, precision)
+    lat0 = torch.from_numpy(g[kind + "_code0"]).reshape(-1)
+    xyz = torch.from_numpy(g[kind + "_batch_pts"][0]).cuda()
+    sdf = torch.from_numpy(g[kind + "_batch_sdf"][0]).reshape(-1).cuda()
+    grad, terms = R.latent_grad(dec, dec.code192(lat0), xyz, sdf, xyz, clamp_dist=0.1, l2reg=True, code_reg_lambda=1e-4,
+                                precision=precision, loss_kind=1)
+    grad, terms = grad.cpu().numpy(), terms.cpu().numpy()
+    ref = g[kind + "_grad0"].reshape(-1)
+    assert grad.shape == (129,) and grad[128] == 0.0  # the stand-in second net contributes nothing
+    assert terms[2] == 0.0 and terms[3] == 0.0       # no occupancy / normal terms in this objective
+    if precision == "fp32":
+        assert abs(terms[0] - float(g[kind + "_loss0"])) < 2e-6
+        assert np.abs(grad[:128] - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7
+    else:
+        # 16-bit forward operands: a rounding error that flips sign(pred - gt) or the clamp gate flips that sample's
+        # whole gradient; 512 samples average less of it out than 30,000 do.  IEEE half is 8x finer than bf16.
+        cos = float(np.dot(grad[:128], ref) / (np.linalg.norm(grad[:128]) * np.linalg.norm(ref)))
+        print(kind, precision, "cos", cos, "max err / max", np.abs(grad[:128] - ref).max() / np.abs(ref).max(), "loss", terms[0], float(g[kind + "_loss0"]))
+        assert abs(terms[0] - float(g[kind + "_loss0"])) < (5e-3 if precision == "bf16" else 1e-3)
+        assert np.abs(grad[:128] - ref).max() <= (0.15 if precision == "bf16" else 0.08) * np.abs(ref).max()
+        assert cos > (0.98 if precision == "bf16" else 0.995)
+
+
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+def test_latent_loop_vs_reference_run(kind):
+    """The device loop fed the mini-batches the reference's run drew reproduces its log and its latent."""
+    from deepjoin_b200 import reconstruct as R
+    g = np.load(os.path.join(G, "deepsdf_reconstruct.npz"))
+    dec = _decoder(0, kind, "fp32")
+    bp, bs = g[kind + "_batch_pts"], g[kind + "_batch_sdf"]
+    iters, ns = bp.shape[0], bp.shape[1]
+    pool_xyz = torch.from_numpy(bp.reshape(-1, 3).copy()).cuda()
+    pool_sdf = torch.from_numpy(bs.reshape(-1).copy()).cuda()
+    sched = torch.arange(iters * ns, dtype=torch.int32).reshape(iters, ns).cuda()
+    log, code = R.optimize_code(dec, dec.code192(torch.from_numpy(g[kind + "_code0"])), pool_xyz, pool_sdf, pool_xyz, sched,
+                                lr=5e-3, lambda1=0.0, lambda3=1.0, clamp_dist=0.1, l2reg=True, code_reg_lambda=1e-4,
+                                precision="fp32", loss_kind=1)
+    log = log.cpu().numpy()
+    assert log.shape == (2, 8) and list(log[:, 0]) == [0, 10]
+    assert np.abs(log[:, 2] - g[kind + "_log_data_loss"]).max() < 2e-5
+    assert np.allclose(log[:, 5], g[kind + "_log_reg_loss"], rtol=1e-3, atol=1e-9)
+    assert np.allclose(log[:, 6], g[kind + "_log_mag"], atol=2e-4)  # |z| AFTER the step (:134-141)
+    assert np.abs(code.cpu().numpy()[:, :128] - g[kind + "_code"]).max() < 2e-3
+    assert float(code[0, 128]) == 0.0
+
+
+def test_reconstruct_deepsdf_dropin_seeded_like_the_reference():
+    from deepjoin_b200.reconstruct_deepsdf import reconstruct
+    g = np.load(os.path.join(G, "deepsdf_reconstruct.npz"))
+    dec = _decoder(0, "default", "fp32")
+    np.random.seed(5)
+    torch.manual_seed(5)
+    loss, lat = reconstruct(dec, 12, 128, (g["xyz"], g["sdf"], {"mask": g["mask"], "broken_gt": None, "percent": 0.0}), 0.01, 0.1,
+                            num_samples=512, lr=5e-3, l2reg=True, code_reg_lambda=1e-4, slippage_method="analytical")
+    assert set(loss) == {"epoch", "data_loss", "reg_loss", "mag"} and loss["epoch"] == [0, 10]
+    assert np.abs(np.asarray(loss["data_loss"]) - g["default_log_data_loss"]).max() < 2e-5
+    assert tuple(lat.shape) == (1, 128) and not lat.is_cuda
+    assert np.abs(lat.numpy() - g["default_code"]).max() < 2e-3
+
+
+def test_reconstruct_deepsdf_tensor_core_run_and_errors():
+    from deepjoin_b200.reconstruct_deepsdf import reconstruct
+    xyz, sdf, _ = synth.make_sample_set(20000, seed=2)
+    mask = xyz[:, 1].astype(np.float32) > -0.2
+    runs = {}
+    for precision in ("fp32", "bf16"):
+        dec = _decoder(0, "trained_norm", precision)
+        assert dec.latent_prec() == {"fp32": "fp32", "bf16": "fp16"}[precision]
+        np.random.seed(1)
+        torch.manual_seed(1)
+        runs[precision] = reconstruct(dec, 60, 128, (xyz, sdf, {"mask": mask}), 0.01, 0.1, num_samples=2000, lr=5e-3,
+                                      l2reg=True, slippage_method="classifier")
+    (loss, lat), (loss32, lat32) = runs["bf16"], runs["fp32"]
+    assert loss["epoch"] == [0, 10, 20, 30, 40, 50] and torch.isfinite(lat).all()
+    print("data_loss bf16", loss["data_loss"], "fp32", loss32["data_loss"])
+    # same seeds, same mini-batches: the tensor-core run (half forward, bf16 backward) tracks the fp32 run
+    assert np.abs(np.asarray(loss["data_loss"]) - np.asarray(loss32["data_loss"])).max() < 2e-2
+    assert loss["data_loss"][-1] < loss["data_loss"][0] - 5e-3 and abs(loss["data_loss"][-1] - loss32["data_loss"][-1]) < 5e-3
+    cos = float((lat * lat32).sum() / (lat.norm() * lat32.norm()))
+    print("cos", cos, "|z|", float(lat.norm()), float(lat32.norm()))
+    assert cos > 0.9
+    with pytest.raises(RuntimeError, match="Unknown slippage method"):
+        reconstruct(dec, 4, 128, (xyz, sdf, {"mask": mask}), 0.01, 0.1, num_samples=100, l2reg=True)
+    with pytest.raises(NotImplementedError):
+        reconstruct(dec, 4, 128, (xyz, sdf, {"percent": 0.1}), 0.01, 0.1, num_samples=100, l2reg=True, slippage_method="analytical")
+    with pytest.raises(UnboundLocalError):  # the reference logs reg_loss without having computed it (:139)
+        reconstruct(dec, 4, 128, (xyz, sdf, {"mask": mask}), 0.01, 0.1, num_samples=100, slippage_method="analytical")

@@ -67,6 +67,24 @@ def test_sample_indices_match_reference_sampler():
         assert np.array_equal(p, g[key + "_pts"]) and np.array_equal(v, g[key + "_vals"])
 
 
+def test_partial_sample_indices_match_reference_sampler():
+    """core.data.select_partial_samples (core/data.py:76-119) on row indices, against the reference's output."""
+    from deepjoin_b200.core import data
+    from deepjoin_b200 import reconstruct_deepsdf as RD
+    g = np.load(os.path.join(G, "deepsdf_reconstruct.npz"))
+    np.random.seed(21)
+    idx = data.select_partial_sample_indices(g["sdf"], g["mask"], 500, uniform_ratio=0.2)
+    assert g["mask"][idx].all()
+    assert np.array_equal(g["xyz"][idx], g["sel_pts"]) and np.array_equal(g["sdf"][idx], g["sel_vals"])
+    np.random.seed(21)
+    p, v = data.select_partial_samples(g["xyz"], g["sdf"], g["mask"], 500, uniform_ratio=0.2)
+    assert np.array_equal(p, g["sel_pts"]) and np.array_equal(v, g["sel_vals"])
+    # the schedule of the whole loop consumes the RNG like the reference loop did (seed 5, 12 x 512)
+    np.random.seed(5)
+    sched = RD.make_schedule(g["sdf"], g["mask"], 12, 512, 0.2)
+    assert np.array_equal(g["xyz"][sched].astype(np.float32), g["default_batch_pts"])
+
+
 def test_sampler_raises_no_samples_error():
     from deepjoin_b200.core import data, errors
     with pytest.raises(errors.NoSamplesError):

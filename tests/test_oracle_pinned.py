@@ -111,3 +111,30 @@ def test_deepsdf_oracle_matches_reference(kind, seed):
     sd = synth.make_deepsdf_state_dict(seed, kind)
     out = O.deepsdf_forward(sd, torch.from_numpy(g["%s_%d_code" % (kind, seed)]), torch.from_numpy(g["%s_%d_pts" % (kind, seed)]))
     assert np.abs(out.numpy() - g["%s_%d_out" % (kind, seed)]).max() < (5e-6 if kind == "default" else 2e-4)
+
+
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+def test_deepsdf_latent_loop_matches_reference(kind):
+    """The oracle's restatement of the baseline's latent loop (reconstruct_deepsdf.py:17-154) against the
+    reference executed in place (tests/golden/make_golden_deepsdf.py): gradient, loss, Adam, logging."""
+    g = np.load(os.path.join(G, "deepsdf_reconstruct.npz"))
+    sd = synth.make_deepsdf_state_dict(0, kind)
+    bp, bs = g[kind + "_batch_pts"], g[kind + "_batch_sdf"]
+    lat0 = torch.from_numpy(g[kind + "_code0"])
+    grad, terms = O.deepsdf_latent_grad(sd, lat0, torch.from_numpy(bp[0]), torch.from_numpy(bs[0]))
+    ref = g[kind + "_grad0"].reshape(-1)
+    assert abs(terms[0] - float(g[kind + "_loss0"])) < 1e-6
+    assert np.abs(grad.numpy() - ref).max() <= 2e-3 * np.abs(ref).max() + 1e-7
+    log, code = O.deepsdf_adam_loop(sd, lat0, lambda e: (torch.from_numpy(bp[e]), torch.from_numpy(bs[e])), bp.shape[0], lr=5e-3)
+    assert np.abs(code.numpy() - g[kind + "_code"]).max() < 2e-3
+    assert log["epoch"] == list(g[kind + "_log_epoch"].astype(int))
+    assert np.abs(np.asarray(log["data_loss"]) - g[kind + "_log_data_loss"]).max() < 1e-4
+    assert np.allclose(log["reg_loss"], g[kind + "_log_reg_loss"], rtol=1e-3, atol=1e-9)
+    assert np.allclose(log["mag"], g[kind + "_log_mag"], atol=2e-4)
+
+
+def test_partial_sampler_restatement_matches_reference():
+    g = np.load(os.path.join(G, "deepsdf_reconstruct.npz"))
+    np.random.seed(21)
+    p, v = O.select_partial_samples(g["xyz"], g["sdf"], g["mask"], num_samples=500, uniform_ratio=0.2)
+    assert np.array_equal(p, g["sel_pts"]) and np.array_equal(v, g["sel_vals"])
