@@ -365,9 +365,9 @@ def main():
             "gpu_launches": launches,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 launch (ncu --set full,
-                         # profiles/r01_tc2_forward_256_ncu_full.txt): 6.2 MB of weights + 16.6 MB of the 67 MB
+                         # profiles/r01_tc2_forward_256_ncu_full.txt): 6.3 MB of weights + 14.0 MB of the 67 MB
                          # output volume (the rest is still in L2 when the kernel ends)
-                         "traffic": 22831616 if (args.precision != "fp32" and d == 256) else None,
+                         "traffic": 20361728 if (args.precision != "fp32" and d == 256) else None,
                          "kernel": "tc2_forward_kernel" if args.precision != "fp32" else "sgemm_kernel",
                          "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step); burst %.1f" % (which, burst),
                          "flop_per_query": FLOP_ALG[u]},
