@@ -130,6 +130,16 @@ def marching_cubes(volume, level, gradient_direction="descent"):
     return verts, faces
 
 
+def to_host(t):
+    """CUDA tensor -> numpy array backed by torch's pinned-memory pool (link-rate copy, no page faults on a fresh
+    allocation; the block is recycled when the array is dropped); larger results go to pageable memory."""
+    t = t.detach().contiguous()
+    pin = t.is_cuda and t.numel() * t.element_size() <= _PINNED_MESH_LIMIT
+    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
+    out.copy_(t)
+    return out.numpy()
+
+
 def merge_vertices(vertices, faces):
     """Device-side ``Mesh.merge_vertices`` (trimesh's process=True merge, core/reconstruct.py:189):
     CUDA tensors vertices f64 [V,3] / faces int32 [F,3] -> (merged vertices, re-indexed faces)."""

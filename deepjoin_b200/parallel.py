@@ -165,7 +165,8 @@ def finish_mesh(verts, faces, dims, padding, gradient_direction):
     v = torch.stack([v[:, 1] * sp[1], v[:, 0] * sp[0], v[:, 2] * sp[2]], dim=1) - (0.5 + padding)
     if v.is_cuda:
         v, faces = R.merge_vertices(v, faces)
-        return Mesh(v.cpu().numpy(), faces.cpu().numpy(), process=False)
+        # int64 faces (what the Mesh holds) are made on the device; both arrays land in pinned host memory
+        return Mesh(R.to_host(v), R.to_host(faces.to(torch.int64)), process=False)
     return Mesh(v.numpy(), faces.numpy())
 
 
