@@ -40,6 +40,7 @@ SIGNATURES = {
     "dj_query_all": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_p, c_p]),
     "dj_query_grid": (c_i, [c_p, c_p, c_i, c_i, c_i, c_d, c_d, c_i64, c_i64, c_i, c_i, c_i, c_i, c_p, c_p]),
     "dj_decode_samples_host": (c_i, [c_p, c_p, c_p, c_i64, c_i, c_i, c_i, c_i, c_p]),
+    "dj_decode_samples_host_strided": (c_i, [c_p, c_p, c_p, c_i64, c_i64, c_i64, c_i, c_i, c_i, c_i, c_p]),
     "dj_latent_grad": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i64, ctypes.POINTER(LatentCfg), c_p, c_p, c_p]),
     "dj_latent_optimize": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, ctypes.POINTER(LatentCfg), c_p, c_p]),
     "dj_latent_optimize_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(LatentCfg), c_p, c_p]),

@@ -53,14 +53,22 @@ def decode_samples(vec, decoder, pts, use_net=1, batch_size=2 ** 16, sigmoid=Tru
         raise RuntimeError("Requested output from non-existent network: {}".format(use_net))
     dev = _device_of(decoder)
     pack = decoder.pack(dev)
-    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    pts = np.asarray(pts, dtype=np.float64)
     if pts.ndim != 2 or pts.shape[1] != 3:
         raise ValueError("pts must be [P, 3]")
-    out = np.empty((pts.shape[0], 1), dtype=np.float64)
+    n = pts.shape[0]
+    strides = (pts.strides[0] // 8, pts.strides[1] // 8)
+    # rows, or the three coordinate arrays behind get_query_points' np.vstack(...).T: passed as they lie
+    if not (strides == (3, 1) or (strides[0] == 1 and strides[1] >= n and n > 1)):
+        pts = np.ascontiguousarray(pts)
+        strides = (3, 1)
+    # the result lands directly in an array from torch's pinned pool (no staging copy, no page faults)
+    out = torch.empty((pts.shape[0], 1), dtype=torch.float64,
+                      pin_memory=0 < pts.shape[0] * 8 <= _PINNED_MESH_LIMIT).numpy()
     code = _code_host(vec)
-    _lib.check(_lib.lib().dj_decode_samples_host(
-        pack.handle, code.ctypes.data, pts.ctypes.data, pts.shape[0], int(use_net), int(bool(decoder._return_occ)),
-        int(bool(sigmoid)), decoder._prec(), out.ctypes.data))
+    _lib.check(_lib.lib().dj_decode_samples_host_strided(
+        pack.handle, code.ctypes.data, pts.ctypes.data, n, strides[0], strides[1], int(use_net),
+        int(bool(decoder._return_occ)), int(bool(sigmoid)), decoder._prec(), out.ctypes.data))
     return out
 
 
@@ -89,8 +97,8 @@ def decode_shape_device(vec, decoder, dims, use_net=1, padding=0.0, sigmoid=True
 
 def decode_shape(vec, decoder, dims, use_net=1, batch_size=2 ** 16, padding=0.0, reshape=True, sigmoid=True):
     """core/reconstruct.py:45-86: values over the np.meshgrid('xy') grid, float64."""
-    values = decode_shape_device(vec, decoder, dims, use_net, padding, sigmoid).cpu().numpy()
-    values = values.astype(np.float64).reshape(-1, 1)
+    # float64 (what the reference returns) is made on the device and copied into pinned host memory
+    values = to_host(decode_shape_device(vec, decoder, dims, use_net, padding, sigmoid).to(torch.float64)).reshape(-1, 1)
     if reshape:
         return values.reshape([d for d in dims]).T
     return values

@@ -1,5 +1,6 @@
 // C ABI of deepjoin_b200 (see include/deepjoin_b200.h): weight packing, launch orchestration.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+#include <thread>
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
@@ -49,6 +50,7 @@ struct DjPack {
   simt::FoldParams fold{};
   // workspaces (grow only)
   DevBuf ws_fwd, ws_lat, ws_host, ws_vol, ws_mask;
+  PinBuf pin_host;  // staging of dj_decode_samples_host
   bool tc_attr_set = false, tc_attr_set2 = false;
   int tc_cluster = 2;  // CTAs sharing one weight stream (1, 2 or 4); env DEEPJOIN_B200_CLUSTER
 };
@@ -78,6 +80,7 @@ static void free_pack(DjPack* p) {
   p->ws_fwd.release();
   p->ws_lat.release();
   p->ws_host.release();
+  p->pin_host.release();
   p->ws_vol.release();
   p->ws_mask.release();
   delete p;
@@ -685,32 +688,70 @@ extern "C" int dj_query_grid(DjPack* p, const float* code_dev, int d0, int d1, i
   return run_forward(p, code_dev, nullptr, G, r_hi - r_lo, H, net_mask_for(use_net), precision, out_dev, (cudaStream_t)stream);
 }
 
-extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const double* pts_host, int64_t n, int use_net,
-                                      int return_occ, int apply_sigmoid, int precision, double* out_host) {
+// memcpy split over a few host threads (one core moves ~10 GB/s; the staging copies of a 256^3 query are 0.5 GB)
+static void par_memcpy(void* dst, const void* src, size_t bytes) {
+  const int nt = bytes >= ((size_t)8 << 20) ? 4 : 1;
+  if (nt == 1) { memcpy(dst, src, bytes); return; }
+  std::vector<std::thread> th;
+  const size_t per = ((bytes / nt) + 4095) & ~(size_t)4095;
+  for (int t = 0; t < nt; t++) {
+    const size_t o = (size_t)t * per;
+    if (o >= bytes) break;
+    const size_t m = std::min(per, bytes - o);
+    th.emplace_back([=] { memcpy((uint8_t*)dst + o, (const uint8_t*)src + o, m); });
+  }
+  for (auto& t : th) t.join();
+}
+static bool is_pinned_host(const void* q) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, q) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+extern "C" int dj_decode_samples_host_strided(DjPack* p, const float* code_host, const double* pts_host, int64_t n,
+                                              int64_t pt_stride, int64_t dim_stride, int use_net, int return_occ,
+                                              int apply_sigmoid, int precision, double* out_host) {
   if (!p || !code_host || (!pts_host && n > 0) || (!out_host && n > 0) || n < 0) return fail(DJ_ERR_INVALID, "dj_decode_samples_host: bad argument");
+  // element (i, d) of the points at pts_host[i*pt_stride + d*dim_stride]: rows [n,3] (3, 1), or three coordinate
+  // arrays (1, S >= n) -- what core.reconstruct.get_query_points returns (np.vstack(...).T, core/reconstruct.py:25-30)
+  const bool soa = (pt_stride == 1 && dim_stride >= n && n > 1);
+  if (!soa && !(pt_stride == 3 && dim_stride == 1) && n > 0)
+    return fail(DJ_ERR_UNSUPPORTED, "dj_decode_samples_host: point strides (%lld, %lld) are neither rows nor coordinate arrays", (long long)pt_stride, (long long)dim_stride);
   if (use_net < 0 || use_net > 3) return fail(DJ_ERR_BAD_NET, "Requested output from non-existent network: %d", use_net);
   DeviceGuard g(p->device);
-  // chunks of 2^21 points ping-pong over two streams / two workspace halves, so that chunk k+1's upload (f64
-  // points, PCIe) overlaps chunk k's decoder kernel and download
+  // Software pipeline over chunks of 2^21 points, two slots.  Pageable host arrays are staged through pinned
+  // memory by this thread (a cudaMemcpyAsync on pageable memory blocks the caller and serialises the chunks);
+  // arrays that are already pinned (the Python wrapper takes its output from the pinned pool) are DMA targets as
+  // they are.  Slot s is reused by chunk k+2 after chunk k's event: its download is then complete.
   const int64_t CH = 1 << 21;
   const int64_t c = std::min<int64_t>(CH, std::max<int64_t>(n, 1));
   const int nc = p->L + p->Lb;
-  // [code | 2 x (pts f64 | pts f32 | out f32 | out f64)]
+  // device: [code | 2 x (pts f64 | pts f32 | out f32 | out f64)]
   const size_t o_p64 = 0, o_p32 = o_p64 + (size_t)c * 24, o_o32 = o_p32 + (size_t)c * 12,
                o_o64 = (o_o32 + (size_t)c * 4 + 15) & ~(size_t)15, half = (o_o64 + (size_t)c * 8 + 255) & ~(size_t)255;
   DJ_CUDA(p->ws_host.reserve(1024 + 2 * half));
   uint8_t* w0 = p->ws_host.as<uint8_t>();
+  const bool stage_in = n > 0 && !is_pinned_host(pts_host), stage_out = n > 0 && !is_pinned_host(out_host);
+  // pinned: [code 1 KB | 2 x (pts f64 | out f64)]
+  const size_t ph = (size_t)c * 32;
+  DJ_CUDA(p->pin_host.reserve(1024 + 2 * ph));
+  uint8_t* h0 = p->pin_host.as<uint8_t>();
+  memcpy(h0, code_host, nc * sizeof(float));
   cudaStream_t sts[2] = {nullptr, nullptr};
-  for (int i = 0; i < 2; i++) DJ_CUDA(cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking));
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  for (int i = 0; i < 2; i++) {
+    DJ_CUDA(cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking));
+    DJ_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+  }
   auto cleanup = [&](int rc) {
     for (int i = 0; i < 2; i++) {
       cudaStreamSynchronize(sts[i]);
       cudaStreamDestroy(sts[i]);
+      cudaEventDestroy(done[i]);
     }
     return rc;
   };
-  if (cudaMemcpyAsync(w0, code_host, nc * sizeof(float), cudaMemcpyHostToDevice, sts[0]) != cudaSuccess ||
-      cudaStreamSynchronize(sts[0]) != cudaSuccess)
+  if (cudaMemcpyAsync(w0, h0, nc * sizeof(float), cudaMemcpyHostToDevice, sts[0]) != cudaSuccess)
     return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: code upload failed"));
   {  // the fold writes the pack's shared tables: once, before either stream launches a decoder kernel
     int rc = launch_fold(p, (const float*)w0, sts[0]);
@@ -718,29 +759,62 @@ extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const d
     if (cudaStreamSynchronize(sts[0]) != cudaSuccess) return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: fold failed"));
   }
   HeadCfg H{OUT_SINGLE, use_net, return_occ, apply_sigmoid, p->desc.slope};
-  int k = 0;
-  for (int64_t s = 0; s < n; s += CH, k++) {
-    const int64_t m = std::min(CH, n - s);
+  const int64_t nchunks = (n + CH - 1) / CH;
+  // chunk j's results leave its slot (after its event)
+  auto retire = [&](int64_t j) -> int {
+    const int slot = (int)(j & 1);
+    if (cudaEventSynchronize(done[slot]) != cudaSuccess) return fail(DJ_ERR_CUDA, "dj_decode_samples_host: chunk %lld failed: %s", (long long)j, cudaGetErrorString(cudaGetLastError()));
+    if (stage_out) par_memcpy(out_host + j * CH, h0 + 1024 + (size_t)slot * ph + (size_t)c * 24, (size_t)std::min(CH, n - j * CH) * 8);
+    return DJ_OK;
+  };
+  for (int64_t k = 0; k < nchunks; k++) {
+    const int64_t s = k * CH, m = std::min(CH, n - s);
+    const int slot = (int)(k & 1);
+    int rc;
+    if (k >= 2 && (rc = retire(k - 2))) return cleanup(rc);
     // the fp32 path works in one shared activation workspace: it stays on one stream
-    const int lane = (precision != DJ_PREC_FP32) ? (k & 1) : 0;
-    cudaStream_t st = sts[lane];
-    uint8_t* w = w0 + 1024 + (size_t)lane * half;
-    if (cudaMemcpyAsync(w + o_p64, pts_host + 3 * s, (size_t)m * 24, cudaMemcpyHostToDevice, st) != cudaSuccess)
-      return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: upload failed"));
-    simt::f64_to_f32_kernel<<<ceil_div(3 * m, 256), 256, 0, st>>>((const double*)(w + o_p64), (float*)(w + o_p32), 3 * m);
+    cudaStream_t st = sts[(precision != DJ_PREC_FP32) ? slot : 0];
+    uint8_t* w = w0 + 1024 + (size_t)slot * half;
+    uint8_t* hs = h0 + 1024 + (size_t)slot * ph;
+    if (soa) {  // three coordinate runs of m doubles -> device [3][m]
+      for (int dd = 0; dd < 3; dd++) {
+        const void* src = pts_host + (size_t)dd * dim_stride + s;
+        if (stage_in) { par_memcpy(hs + (size_t)dd * m * 8, src, (size_t)m * 8); src = hs + (size_t)dd * m * 8; }
+        if (cudaMemcpyAsync(w + o_p64 + (size_t)dd * m * 8, src, (size_t)m * 8, cudaMemcpyHostToDevice, st) != cudaSuccess)
+          return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: upload failed"));
+      }
+      simt::soa_f64_to_xyz_f32_kernel<<<ceil_div(3 * m, 256), 256, 0, st>>>((const double*)(w + o_p64), (float*)(w + o_p32), m);
+    } else {
+      const void* src = pts_host + 3 * s;
+      if (stage_in) { par_memcpy(hs, src, (size_t)m * 24); src = hs; }
+      if (cudaMemcpyAsync(w + o_p64, src, (size_t)m * 24, cudaMemcpyHostToDevice, st) != cudaSuccess)
+        return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: upload failed"));
+      simt::f64_to_f32_kernel<<<ceil_div(3 * m, 256), 256, 0, st>>>((const double*)(w + o_p64), (float*)(w + o_p32), 3 * m);
+    }
     DJ_LAUNCHED();
-    int rc = run_forward(p, (const float*)w0, (const float*)(w + o_p32), GridSpec{}, m, H, net_mask_for(use_net),
-                         precision, (float*)(w + o_o32), st, false);
+    rc = run_forward(p, (const float*)w0, (const float*)(w + o_p32), GridSpec{}, m, H, net_mask_for(use_net),
+                     precision, (float*)(w + o_o32), st, false);
     if (rc) return cleanup(rc);
     simt::f32_to_f64_kernel<<<ceil_div(m, 256), 256, 0, st>>>((const float*)(w + o_o32), (double*)(w + o_o64), m);
     DJ_LAUNCHED();
-    if (cudaMemcpyAsync(out_host + s, w + o_o64, (size_t)m * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+    void* dst = stage_out ? (void*)(hs + (size_t)c * 24) : (void*)(out_host + s);
+    if (cudaMemcpyAsync(dst, w + o_o64, (size_t)m * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess)
       return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: download failed"));
+    if (cudaEventRecord(done[slot], st) != cudaSuccess) return cleanup(fail(DJ_ERR_CUDA, "dj_decode_samples_host: event failed"));
+  }
+  for (int64_t j = std::max<int64_t>(0, nchunks - 2); j < nchunks; j++) {
+    int rc = retire(j);
+    if (rc) return cleanup(rc);
   }
   int rc = cleanup(DJ_OK);
   if (rc) return rc;
   if (precision != DJ_PREC_FP32) return check_err_word(p, 0);
   return DJ_OK;
+}
+
+extern "C" int dj_decode_samples_host(DjPack* p, const float* code_host, const double* pts_host, int64_t n, int use_net,
+                                      int return_occ, int apply_sigmoid, int precision, double* out_host) {
+  return dj_decode_samples_host_strided(p, code_host, pts_host, n, 3, 1, use_net, return_occ, apply_sigmoid, precision, out_host);
 }
 
 // ====================================================================== latent optimisation

@@ -68,6 +68,15 @@ __global__ void f64_to_f32_kernel(const double* __restrict__ in, float* __restri
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g < n) out[g] = (float)in[g];
 }
+// points stored as three coordinate arrays [3][m] (the memory behind np.vstack(...).T) -> [m,3] float32
+__global__ void soa_f64_to_xyz_f32_kernel(const double* __restrict__ in, float* __restrict__ out, int64_t m) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g < 3 * m) {
+    const int64_t i = g / 3;
+    const int d = (int)(g - 3 * i);
+    out[g] = (float)in[(int64_t)d * m + i];
+  }
+}
 __global__ void f32_to_f64_kernel(const float* __restrict__ in, double* __restrict__ out, int64_t n) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g < n) out[g] = (double)in[g];

@@ -103,6 +103,12 @@ int dj_query_grid(DjPack* pack, const float* code_dev, int d0, int d1, int d2, d
 int dj_decode_samples_host(DjPack* pack, const float* code_host, const double* pts_host, int64_t n,
                            int use_net, int return_occ, int apply_sigmoid, int precision,
                            double* out_host);
+/* same; element (i, d) of the points at pts_host[i*pt_stride + d*dim_stride] (in doubles): (3, 1) = rows, or
+ * (1, S) = three coordinate arrays S apart -- the memory behind get_query_points' np.vstack(...).T
+ * (core/reconstruct.py:25-30), which the reference slices row-wise (:113); no host-side transposition. */
+int dj_decode_samples_host_strided(DjPack* pack, const float* code_host, const double* pts_host, int64_t n,
+                                   int64_t pt_stride, int64_t dim_stride, int use_net, int return_occ,
+                                   int apply_sigmoid, int precision, double* out_host);
 
 /* ---- latent-code optimisation ---------------------------------------------------
  * replaces: the body of reconstruct()  (reconstruct.py:107-226) */

@@ -167,6 +167,19 @@ def test_decode_samples_host_buffers(precision):
         out = R.decode_samples(code, dec, pts, use_net=u, batch_size=2 ** 10, sigmoid=sig)
         assert out.dtype == np.float64 and out.shape == ref.shape
         assert np.abs(out - ref).max() <= SDF_TOL[precision]
+    # point layouts: rows, the three coordinate arrays behind get_query_points' np.vstack(...).T (passed as they
+    # lie), float32 input, an arbitrary strided view; several pipeline chunks (2^21 points each) with a ragged tail
+    n = (1 << 22) + 12345
+    big = np.vstack([c for c in (synth.make_points(n, 5).numpy().astype(np.float64).T)]).T
+    assert big.strides == (8, 8 * n)
+    a = R.decode_samples(code, dec, big, use_net=1, sigmoid=False)
+    b = R.decode_samples(code, dec, np.ascontiguousarray(big), use_net=1, sigmoid=False)
+    assert np.array_equal(a, b)
+    sub = big[::7]
+    c = R.decode_samples(code, dec, sub, use_net=1, sigmoid=False)
+    assert np.array_equal(c, a[::7])
+    d = R.decode_samples(code, dec, big[:1000].astype(np.float32), use_net=1, sigmoid=False)
+    assert np.array_equal(d, a[:1000])
 
 
 def test_large_grid_properties_256():
