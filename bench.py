@@ -124,6 +124,8 @@ def run_reference(args):
     if rank != 0:
         return
     import torch
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+    torch.set_num_threads(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     sample = 1 << 17
     rates = []
     for _ in range(args.warmup):
