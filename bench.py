@@ -272,9 +272,12 @@ def main():
         def run_shapes(n_it):
             """configs[2] on this rank: draw every shape's mini-batch schedule on the device, optimise all codes with
             one fused launch per Adam iteration, then extract each shape's restoration mesh."""
+            w_s = time.perf_counter()
             for sh in range(n_sh):
                 _lib.check(_lib.lib().dj_sample_schedule(pools[sh][1].data_ptr(), pools[sh][1].shape[0], n_it, ns_l, 0.2,
                                                          1000 + rank * n_sh + sh, sched[sh].data_ptr(), _lib.stream_ptr()))
+            torch.cuda.synchronize()
+            run_shapes.sched_ms = 1e3 * (time.perf_counter() - w_s)
             codes0 = []
             for sh in range(n_sh):
                 torch.manual_seed(rank * n_sh + sh)
@@ -288,12 +291,14 @@ def main():
             torch.cuda.synchronize()
             run_shapes.opt_ms = t_a.elapsed_time(t_b)
             n_ok = 0
+            w_m = time.perf_counter()
             for sh in range(n_sh):
                 try:
                     R.create_mesh(codes[sh], dec, 2, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
                     n_ok += 1
                 except Exception:  # IsosurfaceExtractionError -> empty mesh, as the reference's mesh_chunk does
                     pass
+            run_shapes.mesh_ms = 1e3 * (time.perf_counter() - w_m)
             return logs, n_ok
 
         run_shapes(10)
@@ -313,7 +318,8 @@ def main():
                                   "mesh per shape" % (n_sh, iters_l, ns_l, d),
                       "shapes_per_s": world * n_sh / (float(tl[0]) * 1e-3), "ms_per_shape": float(tl[0]) / n_sh,
                       "wall_ms_per_shape": 1e3 * (time.perf_counter() - wl) / n_sh, "meshes_with_surface": n_mesh,
-                      "adam_loop_ms_per_shape": run_shapes.opt_ms / n_sh,
+                      "adam_loop_ms_per_shape": run_shapes.opt_ms / n_sh, "schedule_ms_per_shape": run_shapes.sched_ms / n_sh,
+                      "mesh_ms_per_shape": run_shapes.mesh_ms / n_sh,
                       "adam_loop_tflops_alg": n_sh * iters_l * ns_l * 11.03e6 / (run_shapes.opt_ms * 1e-3) / 1e12,
                       "loss_first_last_shape0": [float(logs[0, 0, 1]), float(logs[0, -1, 1])], "precision": args.precision}
     slab = None

@@ -96,6 +96,12 @@ struct Params {
 };
 
 // warp transpose-reduce: on return lane L holds sum over the 32 lanes of v[L] (in v[0]) -- 31 shuffles
+// Activation-sign words (LeakyReLU' of the backward): the 64 outputs a thread produces for one chunk are recorded in
+// two 32-bit words, element e of a word at bit 31 - e.  neg = (+0) - pre has its sign bit set exactly when pre > 0
+// (pre = +-0 gives +0), so one funnel shift appends the flag: 1 instruction per element.
+__device__ __forceinline__ uint32_t push_sign(uint32_t w, float neg) { return __funnelshift_l(__float_as_uint(neg), w, 1); }
+__device__ __forceinline__ bool sign_bit(uint32_t w, int e) { return (w >> (31 - e)) & 1u; }
+
 __device__ __forceinline__ float warp_colsum32(float (&v)[32], int lane) {
 #pragma unroll
   for (int off = 16; off >= 1; off >>= 1) {
@@ -345,19 +351,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
 #pragma unroll 1
           for (int j = 0; j < 4; j++) {
             const int c = 2 * j + h;
-            unsigned long long m = 0ull;
+            uint32_t mw[2] = {0u, 0u};  // sign words, see push_sign
 #pragma unroll
             for (int gq = 0; gq < 8; gq++) {
               float v[8];
 #pragma unroll
               for (int f = 0; f < 8; f++) {
                 const float4 t = sTab[c * 64 + gq * 8 + f];
-                v[f] = tc::leaky(fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
-                m |= (unsigned long long)(v[f] > 0.f) << (gq * 8 + f);
+                const float pre = fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w)));
+                v[f] = tc::leaky(pre, slope);
+                mw[gq >> 2] = push_sign(mw[gq >> 2], 0.f - pre);
               }
               tc::st_shared_v4(a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4), ptx::pack_op16x2<F16>(v[0], v[1]),
                                ptx::pack_op16x2<F16>(v[2], v[3]), ptx::pack_op16x2<F16>(v[4], v[5]), ptx::pack_op16x2<F16>(v[6], v[7]));
             }
+            const unsigned long long m = (unsigned long long)mw[0] | ((unsigned long long)mw[1] << 32);
             mrow[(size_t)(L.mask_layer * 4 + j) * 256] = m;
             ptx::fence_proxy_async_smem();
             __syncwarp();
@@ -436,9 +444,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
           if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
           const int col0 = j * NCH + h * 64;
           const int c = 2 * j + h;
-          unsigned long long* mw = mrow + (size_t)(L.mask_layer * 4 + j) * 256;
-          unsigned long long m = 0ull;
-          if (KIND == K_BWD || KIND == K_BWD_SUM || KIND == K_SUM) m = *mw;
+          unsigned long long* mptr = mrow + (size_t)(L.mask_layer * 4 + j) * 256;
+          constexpr bool BWD = (KIND == K_BWD || KIND == K_BWD_SUM || KIND == K_SUM);
+          uint32_t mw[2] = {0u, 0u};  // sign words of this thread's 64 columns (push_sign / sign_bit)
+          if (BWD) {
+            const unsigned long long m = *mptr;
+            mw[0] = (uint32_t)m;
+            mw[1] = (uint32_t)(m >> 32);
+          }
+          const uint64_t neg1 = ptx::pack_f32x2(-1.f, -1.f), zero2 = 0ull;
           uint32_t pk[32];
           float* vf = reinterpret_cast<float*>(r);  // fp32 results in place (column sums)
 #pragma unroll
@@ -448,7 +462,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
 #pragma unroll
               for (int f = 0; f < 8; f++) {
                 const float4 t = sTab[col0 + gq * 8 + f];
-                v[f] = tc::leaky(__uint_as_float(r[gq * 8 + f]) + fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w))), slope);
+                const float pre = __uint_as_float(r[gq * 8 + f]) + fmaf(t.x, x, fmaf(t.y, y, fmaf(t.z, z, t.w)));
+                v[f] = tc::leaky(pre, slope);
+                mw[gq >> 2] = push_sign(mw[gq >> 2], 0.f - pre);
               }
             } else if (KIND == K_FWD) {
               const float4 b0 = *reinterpret_cast<const float4*>(sBias + col0 + gq * 8);
@@ -460,19 +476,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
                 const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
                 const uint64_t t = ptx::add_f32x2(acc, bb[f]);
                 const uint64_t u = ptx::mul_f32x2(t, slope2);
+                const uint64_t ng = ptx::fma_f32x2(t, neg1, zero2);  // (+0) - pre, both lanes
                 v[2 * f] = fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u));
                 v[2 * f + 1] = fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u));
+                mw[gq >> 2] = push_sign(push_sign(mw[gq >> 2], ptx::f32x2_lo(ng)), ptx::f32x2_hi(ng));
               }
             } else {
 #pragma unroll
-              for (int f = 0; f < 8; f++) {
-                const float a = __uint_as_float(r[gq * 8 + f]);
-                v[f] = ((m >> (gq * 8 + f)) & 1ull) ? a : a * slope;  // LeakyReLU'(pre) from the recorded sign
+              for (int f = 0; f < 4; f++) {
+                const uint64_t a2 = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                const uint64_t u2 = ptx::mul_f32x2(a2, slope2);
+                // LeakyReLU'(pre) from the recorded sign
+                v[2 * f] = sign_bit(mw[gq >> 2], (gq & 3) * 8 + 2 * f) ? ptx::f32x2_lo(a2) : ptx::f32x2_lo(u2);
+                v[2 * f + 1] = sign_bit(mw[gq >> 2], (gq & 3) * 8 + 2 * f + 1) ? ptx::f32x2_hi(a2) : ptx::f32x2_hi(u2);
               }
-            }
-            if (KIND == K_FWD || KIND == K_FWD_XYZ) {
-#pragma unroll
-              for (int f = 0; f < 8; f++) m |= (unsigned long long)(v[f] > 0.f) << (gq * 8 + f);
             }
             if (KIND == K_BWD_SUM || KIND == K_SUM) {
 #pragma unroll
@@ -487,7 +504,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) latent_
                                  pk[gq * 4 + 3]);
             }
           }
-          if (KIND == K_FWD || KIND == K_FWD_XYZ) *mw = m;
+          if (!BWD) *mptr = (unsigned long long)mw[0] | ((unsigned long long)mw[1] << 32);
           if (KIND != K_SUM) {
             if (DST == 0) {
               ptx::fence_proxy_async_smem();
