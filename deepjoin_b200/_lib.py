@@ -45,6 +45,7 @@ SIGNATURES = {
     "dj_latent_optimize": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i64, c_p, ctypes.POINTER(LatentCfg), c_p, c_p]),
     "dj_latent_optimize_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(LatentCfg), c_p, c_p]),
     "dj_sample_schedule": (c_i, [c_p, c_i64, c_i, c_i, c_f, ctypes.c_uint64, c_p, c_p]),
+    "dj_host_mt19937_permutation": (c_i, [c_p, c_p, c_i64, c_p]),
     "dj_mc_create": (c_i, [c_i, ctypes.POINTER(c_p)]),
     "dj_mc_destroy": (c_i, [c_p]),
     "dj_mc_count": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_i, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_p]),

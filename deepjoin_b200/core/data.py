@@ -9,6 +9,32 @@ import numpy as np
 from . import errors
 
 
+def _f32(values):
+    """The stored sample sets are float16 (process_sdf2.py:129-133); numpy compares halves in software, 5x slower
+    than float32, and the widening is exact -- the > 0 tests pick the same rows."""
+    values = np.asarray(values)
+    return values.astype(np.float32) if values.dtype == np.float16 else values
+
+
+def _permutation(n):
+    """np.random.permutation(n) on numpy's global legacy generator, same stream and same result, with the shuffle
+    done by the library's int64 loop (dj_host_mt19937_permutation) instead of numpy's byte-wise generic one."""
+    import ctypes
+    from deepjoin_b200 import _lib
+    n = int(n)
+    if n < 65536:  # below this the state hand-over (get_state / set_state, ~0.5 ms) costs more than it saves
+        return np.random.permutation(n)
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        return np.random.permutation(n)
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    out = np.empty(n, dtype=np.int64)
+    _lib.check(_lib.lib().dj_host_mt19937_permutation(key.ctypes.data, ctypes.byref(pos), n, out.ctypes.data))
+    np.random.set_state((state[0], key, pos.value, state[3], state[4]))
+    return out
+
+
 def _uniform_ratio_rows(n_pts, uniform_ratio, randomize=True):
     """Row ids kept by select_uniform_ratio_samples (core/data.py:122-176), in output order."""
     half = int(n_pts / 2)
@@ -17,23 +43,23 @@ def _uniform_ratio_rows(n_pts, uniform_ratio, randomize=True):
         surface_ends_at = half
         if uniform_ratio > 0.5:
             k = int((max_can_select * (1 - uniform_ratio)) / uniform_ratio)
-            sel = np.random.choice(max_can_select, size=(k), replace=False)
+            sel = _permutation(max_can_select)[:k]  # == np.random.choice(max_can_select, size=k, replace=False)
             rows = np.concatenate([sel, np.arange(surface_ends_at, surface_ends_at + max_can_select)])
         else:
             k = int((max_can_select * uniform_ratio) / (1 - uniform_ratio))
-            sel = np.random.choice(max_can_select, size=(k), replace=False) + surface_ends_at
+            sel = _permutation(max_can_select)[:k] + surface_ends_at  # == np.random.choice(.., size=k, replace=False)
             rows = np.concatenate([np.arange(max_can_select), sel])
     else:
         rows = np.arange(n_pts)
     if randomize:
-        rows = rows[np.random.permutation(rows.shape[0])]
+        rows = rows[_permutation(rows.shape[0])]
     return rows
 
 
 def select_sample_indices(values, num_samples=None, uniform_ratio=0.5):
     """Indices such that ``pts[idx], values[idx]`` equals the reference's
     ``select_samples(pts, values, num_samples, uniform_ratio)`` (single value column)."""
-    values = np.asarray(values)
+    values = _f32(values)
     if values.ndim == 2:
         if values.shape[1] != 1:
             raise NotImplementedError("multi-shape value columns")
@@ -73,14 +99,14 @@ def select_partial_sample_indices(values, mask, num_samples=None, uniform_ratio=
     ``select_partial_samples(pts, values, mask, num_samples, uniform_ratio)`` (core/data.py:76-119):
     ratio selection without shuffling, keep the rows where ``mask`` is set (np.intersect1d leaves them
     in ascending row order), permute, then the fair windows."""
-    values = np.asarray(values)
+    values = _f32(values)
     if values.ndim == 2:
         if values.shape[1] != 1:
             raise NotImplementedError("multi-shape value columns")
         values = values[:, 0]
     rows = _uniform_ratio_rows(values.shape[0], uniform_ratio, randomize=False)
     keep = np.intersect1d(rows, np.where(np.asarray(mask).reshape(-1))[0])
-    keep = keep[np.random.permutation(keep.shape[0])]
+    keep = keep[_permutation(keep.shape[0])]
     return keep[_fair_windows(values[keep], num_samples)]
 
 

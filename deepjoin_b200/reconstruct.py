@@ -28,7 +28,7 @@ def make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio=0.2):
     """Row indices of every iteration's mini-batch, consuming numpy's global RNG exactly as the
     reference loop does (reconstruct.py:114-118 -> core/data.py:15-73)."""
     sched = np.empty((num_iterations, num_samples), dtype=np.int32)
-    vals = np.asarray(b_sdf_gt).reshape(-1)
+    vals = _data._f32(np.asarray(b_sdf_gt).reshape(-1))  # widened once, not per iteration
     for e in range(num_iterations):
         sched[e] = _data.select_sample_indices(vals, num_samples, uniform_ratio=uniform_ratio)
     return sched

@@ -26,7 +26,7 @@ LOSS_DEEPSDF = 1
 def make_schedule(data_sdf, mask, num_iterations, num_samples, uniform_ratio=0.2):
     """Row indices of every iteration's mini-batch (reconstruct_deepsdf.py:102-108 -> core/data.py:76-119)."""
     sched = np.empty((num_iterations, num_samples), dtype=np.int32)
-    vals = np.asarray(data_sdf).reshape(-1)
+    vals = _data._f32(np.asarray(data_sdf).reshape(-1))  # widened once, not per iteration
     for e in range(num_iterations):
         sched[e] = _data.select_partial_sample_indices(vals, mask, num_samples, uniform_ratio=uniform_ratio)
     return sched

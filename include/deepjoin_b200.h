@@ -159,6 +159,11 @@ int dj_latent_optimize_batch(DjPack* pack, int n_shapes, float* codes_dev, float
                              const float* const* pool_nrm_dev, const int64_t* pool_n, const int32_t* idx_dev,
                              const DjLatentCfg* cfg, float* log_dev, void* stream);
 
+/* host-only helper of the reference-exact sampler (core/data.py:141-176): numpy's legacy
+ * RandomState.permutation(n) -- arange(n) shuffled by mtrand's _shuffle_raw / random_interval -- continuing the
+ * MT19937 state (key624, *pos) as np.random.get_state() returns it; *pos is updated.  out [n] int64.  No GPU. */
+int dj_host_mt19937_permutation(uint32_t* key624, int32_t* pos, int64_t n, int64_t* out);
+
 /* replaces: core.data.select_samples(pts, values, num_samples, uniform_ratio)
  * (core/data.py:15-73,122-176) for every iteration at once, on the device, from a counter
  * based RNG (same distribution, not numpy's stream): keep the surface half, a random

@@ -85,6 +85,26 @@ def test_partial_sample_indices_match_reference_sampler():
     assert np.array_equal(g["xyz"][sched].astype(np.float32), g["default_batch_pts"])
 
 
+def test_library_permutation_continues_numpys_legacy_stream():
+    """dj_host_mt19937_permutation == np.random.permutation, element for element, and leaves numpy's global
+    generator in the state numpy itself would be in (mid-block positions, several twister refills, cached gaussian)."""
+    from deepjoin_b200.core import data
+    for seed, n in ((0, 65536), (1, 250000), (2, 312500), (3, 70001)):
+        np.random.seed(seed)
+        np.random.rand(seed * 7 + 3)
+        np.random.randn()  # leaves a cached gaussian in the state
+        a, ra, ga = np.random.permutation(n), np.random.randint(1 << 30), np.random.randn()
+        np.random.seed(seed)
+        np.random.rand(seed * 7 + 3)
+        np.random.randn()
+        b, rb, gb = data._permutation(n), np.random.randint(1 << 30), np.random.randn()
+        assert b.dtype == a.dtype and np.array_equal(a, b) and ra == rb and ga == gb
+    np.random.seed(5)
+    c1 = np.random.choice(250000, size=62500, replace=False)
+    np.random.seed(5)
+    assert np.array_equal(c1, data._permutation(250000)[:62500])
+
+
 def test_sampler_raises_no_samples_error():
     from deepjoin_b200.core import data, errors
     with pytest.raises(errors.NoSamplesError):
