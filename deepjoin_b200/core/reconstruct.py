@@ -63,8 +63,7 @@ def decode_samples(vec, decoder, pts, use_net=1, batch_size=2 ** 16, sigmoid=Tru
         pts = np.ascontiguousarray(pts)
         strides = (3, 1)
     # the result lands directly in an array from torch's pinned pool (no staging copy, no page faults)
-    out = torch.empty((pts.shape[0], 1), dtype=torch.float64,
-                      pin_memory=0 < pts.shape[0] * 8 <= _PINNED_MESH_LIMIT).numpy()
+    out = host_empty((pts.shape[0], 1), torch.float64).numpy()
     code = _code_host(vec)
     _lib.check(_lib.lib().dj_decode_samples_host_strided(
         pack.handle, code.ctypes.data, pts.ctypes.data, n, strides[0], strides[1], int(use_net),
@@ -138,12 +137,27 @@ def marching_cubes(volume, level, gradient_direction="descent"):
     return verts, faces
 
 
+def host_empty(shape, dtype):
+    """Uninitialised host tensor for a result that a device->host copy fills: from torch's pinned-memory pool when
+    it is small enough (link-rate DMA, no page faults on first touch, block recycled when the result is dropped),
+    pageable otherwise or when the pool cannot grow."""
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = n * torch.empty((), dtype=dtype).element_size()
+    if 0 < nbytes <= _PINNED_MESH_LIMIT:
+        try:
+            return torch.empty(shape, dtype=dtype, pin_memory=True)
+        except RuntimeError:  # cudaHostAlloc failed: locked-memory limit of the host
+            pass
+    return torch.empty(shape, dtype=dtype)
+
+
 def to_host(t):
     """CUDA tensor -> numpy array backed by torch's pinned-memory pool (link-rate copy, no page faults on a fresh
     allocation; the block is recycled when the array is dropped); larger results go to pageable memory."""
     t = t.detach().contiguous()
-    pin = t.is_cuda and t.numel() * t.element_size() <= _PINNED_MESH_LIMIT
-    out = torch.empty(t.shape, dtype=t.dtype, pin_memory=pin)
+    out = host_empty(t.shape, t.dtype) if t.is_cuda else torch.empty(t.shape, dtype=t.dtype)
     out.copy_(t)
     return out.numpy()
 
@@ -189,9 +203,8 @@ def create_mesh(vec, decoder, use_net, sigmoid=True, level=0.5, gradient_directi
     # host arrays come from torch's pinned-memory pool (blocks are recycled when the mesh is dropped), so the
     # device->host copy runs at link rate and lands directly in the arrays the mesh keeps: float64
     # vertices, int64 faces as trimesh holds them (faces are widened on the device)
-    pin = (nv.value * 24 + nf.value * 24) <= _PINNED_MESH_LIMIT
-    vertices = torch.empty((nv.value, 3), dtype=torch.float64, pin_memory=pin).numpy()
-    faces = torch.empty((nf.value, 3), dtype=torch.int64, pin_memory=pin).numpy()
+    vertices = host_empty((nv.value, 3), torch.float64).numpy()
+    faces = host_empty((nf.value, 3), torch.int64).numpy()
     bad = ctypes.c_int(0)
     _lib.check(L.dj_create_mesh_fetch64(w.handle, vertices.ctypes.data, faces.ctypes.data, ctypes.byref(bad)))
     # trimesh's process=True (:189): the duplicate-vertex merge already ran on the device

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """BASELINE configs[4]: decoder query throughput sweep -- P points (random in the unit cube, resident in HBM) x
 precision x use_net, CodeLength 128 and 256.  One JSON line per case (device-timed, CUDA events).
-Usage: python tools/sweep.py [--max-log2 28]"""
+Usage: python tools/sweep.py [--max-log2 30]"""
 import argparse
 import json
 import os
@@ -9,7 +9,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-FLOP = {128: {0: 3412992, 1: 5518336}, 256: {0: 2 * (3 * 512 + 512 * 512 * 2 + 253 * 512 + 3 * 512 + 256 * 512 + 3 * 512 * 512 + 5 * 512)}}
+F256 = 2 * (3 * 512 + 512 * 512 * 2 + 253 * 512 + 3 * 512 + 256 * 512 + 3 * 512 * 512 + 5 * 512)
+FLOP = {128: {0: 3412992, 1: 5518336}, 256: {0: F256, 1: F256 + 2105344}}
 
 
 def main():
@@ -31,11 +32,11 @@ def main():
         for log2 in range(20, args.max_log2 + 1, 2):
             n = 1 << log2
             pts = torch.rand((n, 3), device=dev) * 1.2 - 0.6
-            for precision in ("bf16", "fp32"):
+            for precision in ("bf16", "fp16", "fp32"):  # fp16: tf32's 10-bit mantissa at the bf16 rate
                 if precision == "fp32" and log2 > args.fp32_max_log2:
                     continue
                 for u in (0, 1):
-                    for _ in range(2):
+                    for _ in range(2 if log2 <= 26 else 1):
                         dec.query(code, pts, use_net=u, precision=precision)
                     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                     reps = 3 if log2 <= 24 else 1
