@@ -137,6 +137,24 @@ def marching_cubes(volume, level, gradient_direction="descent"):
     return verts, faces
 
 
+_pool_warm = False
+
+
+def _warm_pinned_pool():
+    """torch's pinned allocator hands out power-of-two blocks and keeps freed ones; a first request of a size class
+    costs a cudaHostAlloc (milliseconds, and it synchronises).  Touch every class up to 64 MB once (127 MB, ~40 ms)
+    so that later results of any size find a block."""
+    global _pool_warm
+    if _pool_warm:
+        return
+    _pool_warm = True
+    try:
+        blocks = [torch.empty(1 << k, dtype=torch.uint8, pin_memory=True) for k in range(20, 27)]
+        del blocks
+    except RuntimeError:
+        pass
+
+
 def host_empty(shape, dtype):
     """Uninitialised host tensor for a result that a device->host copy fills: from torch's pinned-memory pool when
     it is small enough (link-rate DMA, no page faults on first touch, block recycled when the result is dropped),
@@ -146,6 +164,7 @@ def host_empty(shape, dtype):
         n *= int(d)
     nbytes = n * torch.empty((), dtype=dtype).element_size()
     if 0 < nbytes <= _PINNED_MESH_LIMIT:
+        _warm_pinned_pool()
         try:
             return torch.empty(shape, dtype=dtype, pin_memory=True)
         except RuntimeError:  # cudaHostAlloc failed: locked-memory limit of the host
