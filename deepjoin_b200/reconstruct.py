@@ -34,6 +34,29 @@ def make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio=0.2):
     return sched
 
 
+def make_schedule_surface_interior(b_sdf_gt, num_iterations, num_samples):
+    """Row indices of every iteration's mini-batch for ``sampling_method="surface_interior_only"``
+    (reconstruct.py:60-98): int(0.2 N) of the INTERIOR uniform rows (second half of the sample set, sdf < 0) drawn
+    without replacement (with, if there are too few), then the fair positive / non-positive windows of
+    select_samples over the surface rows (first half, no ratio step, no shuffle); numpy's global RNG consumed
+    exactly as the reference does."""
+    vals = _data._f32(np.asarray(b_sdf_gt).reshape(-1))
+    half = int(vals.shape[0] / 2)
+    uni_rows = half + np.where(vals[half:] < 0)[0]
+    surf_vals = vals[:half]
+    num_uni = int(num_samples * 0.2)
+    num_surf = int(num_samples - num_uni)
+    sched = np.empty((num_iterations, num_samples), dtype=np.int32)
+    for e in range(num_iterations):
+        if num_uni <= uni_rows.shape[0]:
+            uni_inds = _data._permutation(uni_rows.shape[0])[:num_uni]  # == np.random.choice(n, num_uni, replace=False)
+        else:
+            uni_inds = np.random.choice(uni_rows.shape[0], num_uni, replace=True)
+        sched[e, :num_uni] = uni_rows[uni_inds]
+        sched[e, num_uni:] = _data._fair_windows(surf_vals, num_surf)
+    return sched
+
+
 def init_code(latent_size, break_latent_size, stat):
     """reconstruct.py:48-53 (CPU generator, so torch.manual_seed reproduces the reference)."""
     if type(stat) == type(0.1):
@@ -125,8 +148,6 @@ def reconstruct(decoder, num_iterations, latent_size, break_latent_size, test_sd
                 clamp_dist, sampling_method=None, num_samples=30000, lr=5e-4, l2reg=False, code_reg_lambda=1e-4,
                 iter_path=None, loss_version=None):
     decoder.eval()
-    if sampling_method == "surface_interior_only":
-        raise NotImplementedError("sampling_method='surface_interior_only' (partial-view baseline path)")
     dev = next(decoder.parameters()).device
     if dev.type != "cuda":
         raise RuntimeError("deepjoin_b200: the decoder must live on a CUDA device")
@@ -134,12 +155,23 @@ def reconstruct(decoder, num_iterations, latent_size, break_latent_size, test_sd
         raise ValueError("latent sizes do not match the decoder")
     code0 = init_code(latent_size, break_latent_size, stat)
 
-    pts_gt, b_sdf_gt, b_n_gt = test_sdf
+    if sampling_method == "surface_interior_only":
+        # partial-view sampling (:60-98): (pts, sdf) only, no normals -- the reference's normal term would compare
+        # [N,3] with [N,0] and raise, so it is only usable with lambda1 == 0
+        pts_gt, b_sdf_gt = test_sdf
+        if lambda1 != 0:
+            raise RuntimeError("The size of tensor a (3) must match the size of tensor b (0) at non-singleton dimension 1"
+                               " (sampling_method='surface_interior_only' carries no normals: use lambda1=0)")
+        b_n_gt = np.zeros((np.asarray(pts_gt).shape[0], 3), dtype=np.float32)
+    else:
+        pts_gt, b_sdf_gt, b_n_gt = test_sdf
     pool_xyz = torch.from_numpy(np.ascontiguousarray(pts_gt, dtype=np.float32)).to(dev)
     pool_sdf = torch.from_numpy(np.ascontiguousarray(np.asarray(b_sdf_gt).reshape(-1), dtype=np.float32)).to(dev)
     pool_nrm = torch.from_numpy(np.ascontiguousarray(b_n_gt, dtype=np.float32)).to(dev)
 
-    if sampling_method == "device":
+    if sampling_method == "surface_interior_only":
+        sched = torch.from_numpy(make_schedule_surface_interior(b_sdf_gt, num_iterations, num_samples)).to(dev)
+    elif sampling_method == "device":
         sched = torch.empty((num_iterations, num_samples), device=dev, dtype=torch.int32)
         seed = int(np.random.randint(0, 2 ** 31 - 1))
         with torch.cuda.device(dev):

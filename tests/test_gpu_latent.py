@@ -240,3 +240,22 @@ def test_batched_shapes_equal_one_by_one(precision):
         assert np.allclose(a, b, rtol=tol, atol=tol), s
         assert np.abs(codes[s].cpu().numpy() - code1.cpu().numpy().reshape(-1)).max() < (2e-2 if precision == "bf16" else 2e-3), s
     assert not np.allclose(codes[0].cpu().numpy(), codes[1].cpu().numpy(), atol=1e-3)  # really different shapes
+
+
+def test_reconstruct_surface_interior_only_like_the_reference():
+    """sampling_method="surface_interior_only" (reconstruct.py:60-98): same seeds -> the reference's log and code."""
+    from deepjoin_b200.reconstruct import reconstruct
+    g = np.load(os.path.join(G, "reconstruct_surface_interior.npz"))
+    for kind in ("default", "trained_norm"):
+        dec = util.make_decoder(0, kind, precision="fp32")
+        np.random.seed(7)
+        torch.manual_seed(7)
+        loss, code = reconstruct(dec, 12, 128, 64, [g["xyz"], g["sdf"]], 0.01, 0.0, 0.0, 1.0, 0.1,
+                                 sampling_method="surface_interior_only", num_samples=500, lr=5e-3, l2reg=True, code_reg_lambda=1e-4)
+        assert loss["epoch"] == [0, 10] and loss["norm_loss"] == [0.0, 0.0]
+        assert np.abs(np.asarray(loss["loss"]) - g[kind + "_log_loss"]).max() < 1e-4
+        assert np.abs(np.asarray(loss["occ_data_loss"]) - g[kind + "_log_occ_data_loss"]).max() < 1e-4
+        assert np.abs(code.cpu().numpy() - g[kind + "_code"]).max() < 2e-3
+    with pytest.raises(RuntimeError):  # the reference's normal term cannot be evaluated without normals
+        reconstruct(dec, 2, 128, 64, [g["xyz"], g["sdf"]], 0.01, 1.0, 0.0, 1.0, 0.1, sampling_method="surface_interior_only",
+                    num_samples=100, l2reg=True)

@@ -105,6 +105,28 @@ def test_library_permutation_continues_numpys_legacy_stream():
     assert np.array_equal(c1, data._permutation(250000)[:62500])
 
 
+@pytest.mark.parametrize("kind", ["default", "trained_norm"])
+def test_surface_interior_schedule_reproduces_the_reference_run(kind):
+    """sampling_method="surface_interior_only" (reconstruct.py:60-98): the host schedule, fed to the oracle's Adam loop,
+    reproduces the log and the code of the reference's own seeded run (tests/golden/make_golden_partial.py)."""
+    from deepjoin_b200 import reconstruct as R
+    from oracle import decoder_oracle as O, synth
+    g = np.load(os.path.join(G, "reconstruct_surface_interior.npz"))
+    xyz, sdf = g["xyz"].astype(np.float32), g["sdf"].astype(np.float32)
+    np.random.seed(7)
+    torch.manual_seed(7)
+    code0 = R.init_code(128, 64, 0.01)
+    sched = R.make_schedule_surface_interior(g["sdf"], 12, 500)
+    assert sched.shape == (12, 500) and (sdf.reshape(-1)[sched[:, :100]] < 0).all() and (sched[:, :100] >= 2000).all()
+    assert (sched[:, 100:] < 2000).all()
+    net = O.fold(synth.make_state_dict(0, kind))
+    zeros = torch.zeros(500, 3)
+    log, code = O.adam_loop(net, code0, lambda e: (torch.from_numpy(xyz[sched[e]]), torch.from_numpy(sdf[sched[e]]), zeros),
+                            12, lr=5e-3, lambda1=0.0)
+    assert np.abs(np.asarray(log["loss"]) - g[kind + "_log_loss"]).max() < 1e-4
+    assert np.abs(code.numpy() - g[kind + "_code"]).max() < 2e-3
+
+
 def test_sampler_raises_no_samples_error():
     from deepjoin_b200.core import data, errors
     with pytest.raises(errors.NoSamplesError):
