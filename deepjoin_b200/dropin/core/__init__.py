@@ -6,6 +6,6 @@ import importlib
 import sys
 
 _real = importlib.import_module("deepjoin_b200.core")
-for _sub in ("errors", "reconstruct", "data", "utils_multiprocessing", "utils_deepsdf", "metrics"):
+for _sub in ("errors", "reconstruct", "data", "utils_multiprocessing", "utils_deepsdf", "metrics", "workspace", "handler"):
     sys.modules[__name__ + "." + _sub] = importlib.import_module("deepjoin_b200.core." + _sub)
 sys.modules[__name__] = _real

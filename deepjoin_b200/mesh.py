@@ -96,3 +96,23 @@ def load_ply(path):
         v = np.frombuffer(fh.read(nv * 12), dtype="<f4").reshape(-1, 3)
         rec = np.frombuffer(fh.read(nf * 13), dtype=[("n", "u1"), ("i", "<i4", (3,))])
     return Mesh(v, rec["i"], process=False)
+
+
+def load_obj(path):
+    """Reader for Wavefront OBJ triangle meshes (v / f records; f entries may carry /vt/vn suffixes)."""
+    v, f = [], []
+    with open(path, "r") as fh:
+        for line in fh:
+            t = line.split()
+            if not t:
+                continue
+            if t[0] == "v":
+                v.append([float(x) for x in t[1:4]])
+            elif t[0] == "f":
+                ids = [int(x.split("/")[0]) for x in t[1:]]
+                for k in range(1, len(ids) - 1):  # fan-triangulate polygons
+                    f.append([ids[0], ids[k], ids[k + 1]])
+    v = np.asarray(v, dtype=np.float64).reshape(-1, 3)
+    f = np.asarray(f, dtype=np.int64).reshape(-1, 3)
+    f = np.where(f > 0, f - 1, f + len(v))  # 1-based, negative = relative to the end
+    return Mesh(v, f, process=False)

@@ -2,6 +2,7 @@
 sampler index schedule is bit-exact with the reference's sampler, mesh container, grid
 coordinate arithmetic, drop-in import shims."""
 import ctypes
+import json
 import os
 import re
 import subprocess
@@ -284,3 +285,47 @@ def test_deepsdf_dropin_surface():
     assert all(hasattr(utils_deepsdf, n) for n in ("decode_sdf", "create_mesh", "values2mesh"))
     with pytest.raises(RuntimeError):
         dec.eval().pack()  # CPU decoder: no fallback
+
+
+def test_reconstruction_handler_names_and_round_trips(tmp_path):
+    """the result tree and file names of the reference's ReconstructionHandler (core/handler.py:787-860,
+    core/workspace.py:113-203) and load / save of codes, loss logs, value grids and meshes."""
+    from deepjoin_b200.core import errors, handler, workspace
+    from deepjoin_b200.mesh import Mesh
+    exp = str(tmp_path / "mugs")
+    os.makedirs(exp)
+    h = handler.ReconstructionHandler(exp, signiture=[800, 0.005, 30000], name="ours", checkpoint="2000",
+                                      lat_signiture=[800, 0.005])
+    base = os.path.join(exp, "Reconstructions", "ours@2000")
+    assert h.path_code(7) == os.path.join(base, "Codes", "7_800_0.005_.pth")
+    assert h.path_loss(7) == os.path.join(base, "Codes", "7_800_0.005___loss.pth")
+    assert h.path_mesh(7, 2) == os.path.join(base, "Meshes", "7_2_800_0.005_30000_.ply")
+    assert h.path_values(7, 2) == os.path.join(base, "Meshes", "7_2_800_0.005_30000__values.npy")
+    assert h.path_eval(7, 2, 0, "chamfer") == os.path.join(base, "Codes", "7_2_0_chamfer_800_0.005_30000_.npy")
+    assert not os.path.isdir(base)  # nothing is created until asked to
+    assert workspace.get_reconstructions_dir(exp, None, "latest") == os.path.join(exp, "Reconstructions", "latest")
+    assert handler.iterify_path("a/b.pth", 3) == "a/b__iter-3.pth" and handler.lossify_log_path("a/b.pth") == "a/b__loss.pth"
+    code = torch.arange(192, dtype=torch.float32).reshape(1, 192)
+    h.set_code(7, code, save=True)
+    assert os.path.isfile(h.path_code(7))
+    fresh = handler.ReconstructionHandler(exp, [800, 0.005, 30000], "ours", "2000", lat_signiture=[800, 0.005])
+    assert torch.equal(fresh.get_code(7), code)
+    with pytest.raises(FileNotFoundError):
+        fresh.get_code(8)
+    vals = np.random.default_rng(0).random((4, 4, 4))
+    h.set_values(7, 2, vals, save=True)
+    assert np.array_equal(fresh.get_values(7, 2), vals)
+    mesh = Mesh(np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]]), np.array([[0, 1, 2], [0, 2, 3]]), process=False)
+    h.set_mesh(mesh, 7, 2, save=True)
+    back = fresh.get_mesh(7, 2)
+    assert np.array_equal(back.faces, mesh.faces) and np.allclose(back.vertices, mesh.vertices)
+    with pytest.raises(errors.IsosurfaceExtractionError):
+        fresh.get_mesh(7, 3)
+    obj = str(tmp_path / "m.obj")
+    handler.saver(obj, mesh)
+    again = handler.loader(obj)
+    assert np.array_equal(again.faces, mesh.faces) and np.allclose(again.vertices, mesh.vertices)
+    with pytest.raises(RuntimeError, match="Unhandled file type"):
+        handler.loader(str(tmp_path / "x.gif"))
+    json.dump({"NetworkArch": "decoder_deepsdf"}, open(os.path.join(exp, "specs.json"), "w"))
+    assert workspace.load_experiment_specifications(exp)["NetworkArch"] == "decoder_deepsdf"
