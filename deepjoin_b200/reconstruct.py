@@ -91,7 +91,7 @@ def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, la
 
 
 def optimize_codes(decoder, codes0, pools, schedules, lr, lambda1, lambda3, clamp_dist, l2reg=True, code_reg_lambda=1e-4,
-                   log_every=10, precision="bf16"):
+                   log_every=10, precision="bf16", loss_kind=0):
     """The device loop for S independent shapes at once (extension; the reference's worker runs them one after
     the other, core/utils_multiprocessing.py:33-71).  codes0 [S, L+Lb]; pools: S tuples (xyz [M,3], sdf [M],
     nrm [M,3]) of CUDA f32 tensors; schedules CUDA int32 [S, iterations, num_samples].
@@ -106,7 +106,7 @@ def optimize_codes(decoder, codes0, pools, schedules, lr, lambda1, lambda3, clam
     iters, ns = int(schedules.shape[1]), int(schedules.shape[2])
     cfg = _lib.LatentCfg(iters, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
                          float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, int(log_every),
-                         _lib.PREC[precision])
+                         _lib.PREC[precision], int(loss_kind))
     codes = codes0.detach().to(device=dev, dtype=torch.float32).reshape(S, -1).clone().contiguous()
     m = torch.zeros_like(codes)
     v = torch.zeros_like(codes)
