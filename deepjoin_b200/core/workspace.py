@@ -7,19 +7,19 @@ import os
 
 import torch
 
-model_params_subdir = "ModelParameters"
-latent_codes_subdir = "LatentCodes"
-reconstructions_subdir = "Reconstructions"
-reconstruction_meshes_subdir = "Meshes"
-reconstruction_codes_subdir = "Codes"
-reconstruction_stats_subdir = "Stats"
-logs_filename = "Logs.pth"
-specifications_filename = "specs.json"
+# directory / file names inside an experiment (module attributes <key>_subdir, <key>_filename as in the reference)
+_NAMES = {
+    "model_params_subdir": "ModelParameters", "latent_codes_subdir": "LatentCodes",
+    "reconstructions_subdir": "Reconstructions", "reconstruction_meshes_subdir": "Meshes",
+    "reconstruction_codes_subdir": "Codes", "reconstruction_stats_subdir": "Stats",
+    "logs_filename": "Logs.pth", "specifications_filename": "specs.json",
+}
+globals().update(_NAMES)
 
 
 def load_experiment_specifications(experiment_directory):
     """workspace.py:24-32."""
-    filename = os.path.join(experiment_directory, specifications_filename)
+    filename = os.path.join(experiment_directory, _NAMES["specifications_filename"])
     if not os.path.isfile(filename):
         raise Exception("The experiment directory ({}) does not include specifications file ".format(experiment_directory)
                         + '"specs.json"')
@@ -29,7 +29,7 @@ def load_experiment_specifications(experiment_directory):
 
 def load_model_parameters(experiment_directory, checkpoint, decoder):
     """workspace.py:34-42: state dict of ModelParameters/<checkpoint>.pth into ``decoder``; returns the epoch."""
-    filename = os.path.join(experiment_directory, model_params_subdir, checkpoint + ".pth")
+    filename = os.path.join(experiment_directory, _NAMES["model_params_subdir"], checkpoint + ".pth")
     if not os.path.isfile(filename):
         raise Exception('model state dict "{}" does not exist'.format(filename))
     data = torch.load(filename, map_location="cpu", weights_only=False)
@@ -51,13 +51,13 @@ def _made(path, create):
 
 
 def get_model_params_dir(experiment_dir, create_if_nonexistent=False):
-    return _made(os.path.join(experiment_dir, model_params_subdir), create_if_nonexistent)
+    return _made(os.path.join(experiment_dir, _NAMES["model_params_subdir"]), create_if_nonexistent)
 
 
 def get_reconstructions_dir(experiment_directory, name=None, checkpoint="latest", create=False):
     """Reconstructions/<checkpoint> or Reconstructions/<name>@<checkpoint> (workspace.py:113-131)."""
     leaf = str(checkpoint) if name is None else name + "@" + str(checkpoint)
-    return _made(os.path.join(experiment_directory, reconstructions_subdir, leaf), create)
+    return _made(os.path.join(experiment_directory, _NAMES["reconstructions_subdir"], leaf), create)
 
 
 def _reconstructions_sub(sub):
@@ -66,6 +66,6 @@ def _reconstructions_sub(sub):
     return get
 
 
-get_reconstructions_codes_dir = _reconstructions_sub(reconstruction_codes_subdir)     # workspace.py:134-149
-get_reconstructions_stats_dir = _reconstructions_sub(reconstruction_stats_subdir)     # workspace.py:152-167
-get_reconstructions_meshes_dir = _reconstructions_sub(reconstruction_meshes_subdir)   # workspace.py:188-203
+get_reconstructions_codes_dir = _reconstructions_sub(_NAMES["reconstruction_codes_subdir"])     # workspace.py:134-149
+get_reconstructions_stats_dir = _reconstructions_sub(_NAMES["reconstruction_stats_subdir"])     # workspace.py:152-167
+get_reconstructions_meshes_dir = _reconstructions_sub(_NAMES["reconstruction_meshes_subdir"])   # workspace.py:188-203
