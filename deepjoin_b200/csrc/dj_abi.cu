@@ -28,7 +28,6 @@ struct DjPack {
   std::vector<int> f_out, f_in, h_out, h_in;
   float* fWx = nullptr;  // [H, K3+3] = [W_li[:, :K3] | W_li[:, K3+L : K3+L+3]] (fp32 forward of the re-injection layer)
   // tensor-core path
-  uint8_t* stream[2] = {nullptr, nullptr};
   float* bias_dev = nullptr;
   tc::TcNet nets[2];
   // CTA-pair (cta_group::2) program: one weight stream per cluster rank
@@ -43,7 +42,6 @@ struct DjPack {
   int lat_n_prog = 0;
   int lat_net1_lo = 0, lat_net1_hi = 0;  // program entries of the second net (forward + backward)
   bool lat_attr_set = false;
-  int tc_kernel = 2;  // 2: CTA-pair kernel (default); 1: single-CTA kernel (env DEEPJOIN_B200_TC=1)
   // per-call shape constants + device error word
   float4* tables = nullptr;
   unsigned int* err = nullptr;
@@ -51,8 +49,7 @@ struct DjPack {
   // workspaces (grow only)
   DevBuf ws_fwd, ws_lat, ws_host, ws_vol, ws_mask;
   PinBuf pin_host;  // staging of dj_decode_samples_host
-  bool tc_attr_set = false, tc_attr_set2 = false;
-  int tc_cluster = 2;  // CTAs sharing one weight stream (1, 2 or 4); env DEEPJOIN_B200_CLUSTER
+  bool tc_attr_set2 = false;
 };
 
 static void free_pack(DjPack* p) {
@@ -63,7 +60,6 @@ static void free_pack(DjPack* p) {
       if (q) cudaFree(q);
   if (p->fWx) cudaFree(p->fWx);
   for (int i = 0; i < 2; i++) {
-    if (p->stream[i]) cudaFree(p->stream[i]);
     for (int r = 0; r < 2; r++)
       if (p->stream2[i][r]) cudaFree(p->stream2[i][r]);
     for (int r = 0; r < 2; r++)
@@ -186,14 +182,6 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
   p->desc = *d;
   p->device = device;
   p->num_sms = prop.multiProcessorCount;
-  if (const char* e = getenv("DEEPJOIN_B200_CLUSTER")) {
-    const int c = atoi(e);
-    if (c == 1 || c == 2 || c == 4) p->tc_cluster = c;
-  }
-  if (const char* e = getenv("DEEPJOIN_B200_TC")) {
-    const int c = atoi(e);
-    if (c == 1 || c == 2) p->tc_kernel = c;
-  }
   p->L = L; p->Lb = Lb; p->H = H; p->K3 = K3;
   auto bail = [&](int code) { free_pack(p); return code; };
 
@@ -249,7 +237,6 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
   std::vector<float> bias_host;
   for (int net = 0; net < 2; net++) {
     const int nl = net == 0 ? d->f_layers : d->h_layers;
-    const float* const* W = net == 0 ? f_w : h_w;
     const float* const* B = net == 0 ? f_b : h_b;
     const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
     const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
@@ -258,7 +245,6 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     N.n_layers = nl - 1;  // layer 0 runs on CUDA cores
     N.l0_table = net == 0 ? 0 : 2;
     N.head_leaky = net == 1;  // decoder :259-270
-    std::vector<uint8_t> blob;
     int prev_n_chunks = 4;  // layer 0 writes all 8 k-chunks
     for (int l = 1; l < nl; l++) {
       tc::TcLayer& T = N.layers[l - 1];
@@ -277,18 +263,8 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       if (!reinj) {
         for (int j = 0; j < 512; j++) bias_host.push_back(j < n_real ? B[l][j] : 0.f);
       }
-      const int rows = T.mma_n;
-      for (int j = 0; j < T.n_chunks; j++)
-        for (int c = 0; c < T.k_chunks; c++) {
-          const size_t o = blob.size();
-          blob.resize(o + T.stage_bytes);
-          pack_tile(W[l], ins[l], n_real, k_real, j * rows, c * 64, rows, blob.data() + o);
-        }
       prev_n_chunks = T.n_chunks;
     }
-    DJ_TRY(cudaMalloc((void**)&p->stream[net], blob.size()));
-    DJ_TRY(cudaMemcpy(p->stream[net], blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    N.stream = p->stream[net];
   }
   // ---- CTA-pair program: layer 0 as a K = 16 tensor-core layer (point split hi/lo), then the same layers / bias
   // offsets; every 128-row output chunk is split 64/64 between the two CTAs of a pair and a ring stage carries
@@ -538,8 +514,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
   if (n <= 0) return DJ_OK;
   int rc;
   if (do_fold && (rc = launch_fold(p, code_dev, st))) return rc;
-  if (precision == DJ_PREC_FP16 && p->tc_kernel != 2) return fail(DJ_ERR_UNSUPPORTED, "DJ_PREC_FP16 needs the CTA-pair kernel (DEEPJOIN_B200_TC=2)");
-  if ((precision == DJ_PREC_BF16 || precision == DJ_PREC_FP16) && p->tc_kernel == 2) {
+  if (precision == DJ_PREC_BF16 || precision == DJ_PREC_FP16) {
     const bool f16 = precision == DJ_PREC_FP16;
     tc2::Params P;
     memset(&P, 0, sizeof P);
@@ -573,51 +548,6 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else if (P.debug) tc2::tc2_forward_kernel<1, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else tc2::tc2_forward_kernel<0, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
-    DJ_LAUNCHED();
-    return DJ_OK;
-  }
-  if (precision == DJ_PREC_BF16) {
-    tc::TcParams P;
-    memset(&P, 0, sizeof P);
-    P.nets[0] = p->nets[0];
-    P.nets[1] = p->nets[1];
-    P.net_mask = net_mask;
-    P.grid_mode = G.on;
-    if (const char* e = getenv("DEEPJOIN_B200_DEBUG")) P.debug = atoi(e);
-    P.bias = p->bias_dev;
-    P.tables = p->tables;
-    P.xyz = xyz_dev;
-    P.n = n;
-    P.d0 = G.d0; P.d1 = G.d1; P.d2 = G.d2;
-    P.step0 = G.step(G.d0); P.step1 = G.step(G.d1); P.step2 = G.step(G.d2);
-    P.stop = G.stop; P.offs = G.offs; P.r_lo = G.r_lo;
-    P.head = head;
-    P.out = out_dev;
-    P.err = p->err;
-    const int64_t ntiles = (n + tc::TILE_M - 1) / tc::TILE_M;
-    int cluster = p->tc_cluster;
-    int grid = (int)std::min<int64_t>((ntiles + cluster - 1) / cluster * cluster, p->num_sms / cluster * cluster);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(tc::NTHREADS);
-    cfg.dynamicSmemBytes = tc::SMEM_BYTES;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    auto kern = cluster == 4 ? tc::tc_forward_kernel<4> : (cluster == 2 ? tc::tc_forward_kernel<2> : tc::tc_forward_kernel<1>);
-    if (!p->tc_attr_set) {
-      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-      DJ_CUDA(cudaFuncSetAttribute(tc::tc_forward_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SMEM_BYTES));
-      p->tc_attr_set = true;
-    }
-    DJ_CUDA(cudaLaunchKernelEx(&cfg, kern, P));
     DJ_LAUNCHED();
     return DJ_OK;
   }

@@ -3,7 +3,7 @@
 mkdir -p gpurun_out
 for cfg in ${CFGS:-"2 0" "2 1" "2 2" "2 3" "1 0"}; do
   set -- ${cfg/_/ }
-  DEEPJOIN_B200_TC=$1 DEEPJOIN_B200_CLUSTER=1 DEEPJOIN_B200_DEBUG=$2 timeout 300 python bench.py --steps 3 --warmup 3 --query-only > gpurun_out/dbg_$1_$2.log 2>&1
+  DEEPJOIN_B200_DEBUG=$2 timeout 300 python bench.py --steps 3 --warmup 3 --query-only > gpurun_out/dbg_$1_$2.log 2>&1
   python - <<PY
 import json
 try:
