@@ -255,7 +255,7 @@ def test_grid_mode_equals_point_mode_for_any_dims_rows_and_branch():
     decs = {p: util.make_decoder(1, "trained_norm", precision=p) for p in ("bf16", "fp16", "fp32")}
     code = util.trained_code(1).cuda()
 
-    @settings(max_examples=40, deadline=None)
+    @settings(max_examples=40, deadline=None, derandomize=True, database=None)
     @given(d0=st.integers(2, 24), d1=st.integers(2, 24), d2=st.integers(2, 24), padding=st.sampled_from([0.0, 0.05, 0.1, 0.3]),
            u=st.sampled_from([0, 1, 2, 3]), precision=st.sampled_from(["bf16", "fp16", "fp32"]), cut=st.tuples(st.floats(0, 1), st.floats(0, 1)))
     def run(d0, d1, d2, padding, u, precision, cut):

@@ -103,7 +103,7 @@ def test_random_volumes_levels_and_quantised_values_bit_exact():
     faces and float32 vertices identical to the sequential sweep, or the same error."""
     from hypothesis import given, settings, strategies as st
 
-    @settings(max_examples=60, deadline=None)
+    @settings(max_examples=60, deadline=None, derandomize=True, database=None)
     @given(seed=st.integers(0, 10 ** 6), n0=st.integers(2, 12), n1=st.integers(2, 12), n2=st.sampled_from([2, 3, 7, 33, 300]),
            level=st.sampled_from([0.0, 0.25, -0.5, 0.1234]), quant=st.sampled_from([0, 4, 2]), direction=st.sampled_from(["ascent", "descent"]))
     def run(seed, n0, n1, n2, level, quant, direction):
