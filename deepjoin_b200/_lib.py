@@ -10,7 +10,8 @@ from .core import errors
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdeepjoin_b200.so")
 
-OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SURFACE, ERR_LEVEL_RANGE, ERR_NO_SAMPLES, ERR_BAD_NET, ERR_DEVICE = range(9)
+(OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SURFACE, ERR_LEVEL_RANGE, ERR_NO_SAMPLES, ERR_BAD_NET, ERR_DEVICE,
+ ERR_PERMISSION, ERR_IO) = range(11)
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2}
 
 c_i, c_i64, c_d, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_float, ctypes.c_void_p
@@ -46,6 +47,8 @@ SIGNATURES = {
     "dj_latent_optimize_batch": (c_i, [c_p, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, ctypes.POINTER(LatentCfg), c_p, c_p]),
     "dj_sample_schedule": (c_i, [c_p, c_i64, c_i, c_i, c_f, ctypes.c_uint64, c_p, c_p]),
     "dj_host_mt19937_permutation": (c_i, [c_p, c_p, c_i64, c_p]),
+    "dj_host_write_ply": (c_i, [ctypes.c_char_p, c_p, c_i64, c_p, c_i64]),
+    "dj_host_write_obj": (c_i, [ctypes.c_char_p, c_p, c_i64, c_p, c_i64]),
     "dj_mc_create": (c_i, [c_i, ctypes.POINTER(c_p)]),
     "dj_mc_destroy": (c_i, [c_p]),
     "dj_mc_count": (c_i, [c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_d, c_i, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64), c_p]),
@@ -102,6 +105,10 @@ def check(rc):
         raise NotImplementedError(msg)
     if rc == ERR_INVALID:
         raise ValueError(msg)
+    if rc == ERR_PERMISSION:
+        raise PermissionError(msg)
+    if rc == ERR_IO:
+        raise OSError(msg)
     raise RuntimeError("deepjoin_b200 [%d]: %s" % (rc, msg))
 
 

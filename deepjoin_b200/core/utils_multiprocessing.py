@@ -40,14 +40,38 @@ def _todo(path, overwrite):
 
 
 def _each(chunk_inputs, chunk_paths, overwrite, callback, work):
-    """The shared item loop of both workers: skip finished items, report progress."""
-    for item, path in zip(chunk_inputs, chunk_paths):
-        if _todo(path, overwrite):
-            work(item, path)
-        else:
-            _log.debug("Skipping %s", path)
+    """The shared item loop of both workers: skip finished items, report progress.  ``work`` may return a callable
+    with the host-only rest of the item (exporting a mesh): it runs on a background thread while the next item's GPU
+    work is enqueued, at most one in flight; progress is reported when an item is really finished."""
+    import threading
+
+    def done():
         if callback is not None:
             callback()
+
+    pending, pending_path = None, None
+    for item, path in zip(chunk_inputs, chunk_paths):
+        if pending is not None and path == pending_path:  # the same file again: let the first write land
+            pending.join()
+            done()
+            pending = None
+        rest = None
+        if _todo(path, overwrite):
+            rest = work(item, path)
+        else:
+            _log.debug("Skipping %s", path)
+        if pending is not None:
+            pending.join()
+            done()
+            pending = None
+        if rest is None:
+            done()
+        else:
+            pending, pending_path = threading.Thread(target=rest), path
+            pending.start()
+    if pending is not None:
+        pending.join()
+        done()
 
 
 def reconstruct_chunk(chunk_inputs, chunk_paths, reconstruct_fn, network_kwargs, reconstruction_kwargs,
@@ -86,11 +110,16 @@ def mesh_chunk(chunk_inputs, chunk_paths, mesh_fn, network_kwargs, mesh_kwargs, 
         except PermissionError:
             _log.warning("Could not save: %s", path)
             return
-        if save:
+        if not save:
+            return None
+
+        def export():  # host-only (the library's PLY writer releases the GIL): overlaps the next item's query
             try:
                 _log.debug("Mesh chunker saving to: %s", path)
                 mesh.export(path)
             except PermissionError:
                 _log.warning("Could not save: %s", path)
+
+        return export
 
     _each(chunk_inputs, chunk_paths, overwrite, callback, work)

@@ -1,6 +1,7 @@
 // C ABI of deepjoin_b200 (see include/deepjoin_b200.h): weight packing, launch orchestration.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <thread>
+#include <cerrno>
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
@@ -1002,6 +1003,55 @@ extern "C" int dj_latent_optimize(DjPack* p, float* code_dev, float* adam_m_dev,
                                   void* stream) {
   return dj_latent_optimize_batch(p, 1, code_dev, adam_m_dev, adam_v_dev, &pool_xyz_dev, &pool_sdf_dev, &pool_nrm_dev, &pool_n,
                                   idx_dev, cfg, log_dev, stream);
+}
+
+// ---- host: mesh writers.  The batch meshing worker (core/utils_multiprocessing.py:74-114) exports every mesh it
+// extracts; numpy's record packing took longer (80 ms for 445 k vertices / 857 k faces) than the whole GPU pipeline
+// (69 ms), a Python OBJ loop 4 s.  Same bytes as the Python writers in deepjoin_b200/mesh.py.
+extern "C" int dj_host_write_ply(const char* path, const double* verts, int64_t nv, const int64_t* faces, int64_t nf) {
+  if (!path || nv < 0 || nf < 0 || (nv && !verts) || (nf && !faces)) return fail(DJ_ERR_INVALID, "dj_host_write_ply: bad argument");
+  char header[512];
+  const int hl = snprintf(header, sizeof header,
+                          "ply\nformat binary_little_endian 1.0\ncomment deepjoin_b200\nelement vertex %lld\nproperty float x\n"
+                          "property float y\nproperty float z\nelement face %lld\nproperty list uchar int vertex_indices\nend_header\n",
+                          (long long)nv, (long long)nf);
+  std::vector<uint8_t> buf((size_t)hl + (size_t)nv * 12 + (size_t)nf * 13);
+  memcpy(buf.data(), header, hl);
+  float* vf = reinterpret_cast<float*>(buf.data() + hl);  // header length is not a multiple of 4: write through memcpy
+  uint8_t* q = buf.data() + hl;
+  for (int64_t i = 0; i < 3 * nv; i++) {
+    const float x = (float)verts[i];
+    memcpy(q + 4 * i, &x, 4);
+  }
+  (void)vf;
+  q += (size_t)nv * 12;
+  for (int64_t i = 0; i < nf; i++) {
+    q[0] = 3;
+    const int32_t t[3] = {(int32_t)faces[3 * i], (int32_t)faces[3 * i + 1], (int32_t)faces[3 * i + 2]};
+    memcpy(q + 1, t, 12);
+    q += 13;
+  }
+  FILE* fh = fopen(path, "wb");
+  if (!fh) return fail(errno == EACCES ? DJ_ERR_PERMISSION : DJ_ERR_IO, "dj_host_write_ply: cannot open %s: %s", path, strerror(errno));
+  const size_t wr = fwrite(buf.data(), 1, buf.size(), fh);
+  const int cl = fclose(fh);
+  if (wr != buf.size() || cl != 0) return fail(DJ_ERR_IO, "dj_host_write_ply: short write to %s", path);
+  return DJ_OK;
+}
+
+extern "C" int dj_host_write_obj(const char* path, const double* verts, int64_t nv, const int64_t* faces, int64_t nf) {
+  if (!path || nv < 0 || nf < 0 || (nv && !verts) || (nf && !faces)) return fail(DJ_ERR_INVALID, "dj_host_write_obj: bad argument");
+  FILE* fh = fopen(path, "w");
+  if (!fh) return fail(errno == EACCES ? DJ_ERR_PERMISSION : DJ_ERR_IO, "dj_host_write_obj: cannot open %s: %s", path, strerror(errno));
+  std::vector<char> big(1 << 22);
+  setvbuf(fh, big.data(), _IOFBF, big.size());
+  bool ok = true;
+  for (int64_t i = 0; i < nv && ok; i++) ok = fprintf(fh, "v %.8f %.8f %.8f\n", verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]) > 0;
+  for (int64_t i = 0; i < nf && ok; i++)
+    ok = fprintf(fh, "f %lld %lld %lld\n", (long long)faces[3 * i] + 1, (long long)faces[3 * i + 1] + 1, (long long)faces[3 * i + 2] + 1) > 0;
+  const int cl = fclose(fh);
+  if (!ok || cl != 0) return fail(DJ_ERR_IO, "dj_host_write_obj: short write to %s", path);
+  return DJ_OK;
 }
 
 // ---- host: numpy's legacy RandomState.permutation(n), continuing a given MT19937 state -------------------------

@@ -32,6 +32,8 @@ extern "C" {
 #define DJ_ERR_NO_SAMPLES 6   /* core/data.py:56-59,66-69 -> NoSamplesError       */
 #define DJ_ERR_BAD_NET 7      /* decoder :454-457 RuntimeError("non-existent network") */
 #define DJ_ERR_DEVICE 8       /* kernel-side watchdog / device fault flag         */
+#define DJ_ERR_PERMISSION 9   /* host file not writable -> PermissionError (utils_multiprocessing.py:99-109) */
+#define DJ_ERR_IO 10          /* other host file error -> OSError                 */
 
 /* arithmetic of the hidden layers */
 #define DJ_PREC_FP32 0   /* fp32 CUDA-core path: the reference's own arithmetic (torch fp32 SGEMM) */
@@ -158,6 +160,13 @@ int dj_latent_optimize_batch(DjPack* pack, int n_shapes, float* codes_dev, float
                              const float* const* pool_xyz_dev, const float* const* pool_sdf_dev,
                              const float* const* pool_nrm_dev, const int64_t* pool_n, const int32_t* idx_dev,
                              const DjLatentCfg* cfg, float* log_dev, void* stream);
+
+/* host-only: mesh export as the batch meshing worker does for every item (core/utils_multiprocessing.py:99-109,
+ * core/handler.py:81-126 saver -> mesh.export): binary little-endian PLY (float32 vertices, uchar-counted int32
+ * faces) / Wavefront OBJ ("v %.8f", 1-based "f").  verts [nv,3] float64, faces [nf,3] int64 (the arrays a mesh
+ * holds).  No GPU. */
+int dj_host_write_ply(const char* path, const double* verts, int64_t nv, const int64_t* faces, int64_t nf);
+int dj_host_write_obj(const char* path, const double* verts, int64_t nv, const int64_t* faces, int64_t nf);
 
 /* host-only helper of the reference-exact sampler (core/data.py:141-176): numpy's legacy
  * RandomState.permutation(n) -- arange(n) shuffled by mtrand's _shuffle_raw / random_interval -- continuing the

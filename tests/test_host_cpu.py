@@ -329,3 +329,61 @@ def test_reconstruction_handler_names_and_round_trips(tmp_path):
         handler.loader(str(tmp_path / "x.gif"))
     json.dump({"NetworkArch": "decoder_deepsdf"}, open(os.path.join(exp, "specs.json"), "w"))
     assert workspace.load_experiment_specifications(exp)["NetworkArch"] == "decoder_deepsdf"
+
+
+def test_native_mesh_writers_produce_the_python_writers_bytes(tmp_path):
+    """dj_host_write_ply / dj_host_write_obj (what Mesh.export uses) == the numpy / Python writers, byte for byte;
+    empty meshes; an unwritable path is a PermissionError / OSError as open() would raise."""
+    import filecmp
+    from deepjoin_b200.mesh import Mesh, load_obj, load_ply
+    rng = np.random.default_rng(3)
+    m = Mesh(rng.normal(size=(2500, 3)) * 10.0 ** rng.integers(-6, 3, size=(2500, 1)), rng.integers(0, 2500, (4000, 3)), process=False)
+    for ext, ref in (("ply", m._export_ply_numpy), ("obj", m._export_obj_python)):
+        a, b = str(tmp_path / ("a." + ext)), str(tmp_path / ("b." + ext))
+        m.export(a)
+        ref(b)
+        assert filecmp.cmp(a, b, shallow=False), ext
+    e = str(tmp_path / "empty.ply")
+    Mesh().export(e)
+    assert load_ply(e).is_empty
+    Mesh().export(str(tmp_path / "empty.obj"))
+    assert load_obj(str(tmp_path / "empty.obj")).is_empty
+    with pytest.raises(OSError):  # PermissionError is an OSError
+        m.export(str(tmp_path / "no_such_dir" / "x.ply"))
+
+
+def test_worker_loop_overlaps_the_deferred_part_and_reports_progress_in_order(tmp_path):
+    """core.utils_multiprocessing._each: the callable an item returns runs in the background while the next item
+    starts; at most one in flight; the callback fires once per item, after the item is really finished; finished
+    items are skipped; a repeated path waits for its first write."""
+    import threading
+    import time
+    from deepjoin_b200.core import utils_multiprocessing as U
+    log, lock = [], threading.Lock()
+
+    def note(x):
+        with lock:
+            log.append(x)
+
+    paths = [str(tmp_path / n) for n in ("a", "b", "done", "c", "c")]
+    open(paths[2], "w").write("x")
+    os.utime(paths[2], (2e9, 2e9))  # newer than the reference's overwrite stamp: a finished item
+
+    def work(item, path):
+        note(("gpu", item))
+
+        def rest():
+            time.sleep(0.05)
+            open(path, "w").write("y")
+            note(("saved", item))
+        return rest
+
+    U._each(list(range(5)), paths, False, lambda: note(("cb", None)), work)
+    kinds = [k for k, _ in log]
+    assert kinds.count("cb") == 5 and [i for k, i in log if k == "gpu"] == [0, 1, 3]   # item 2 finished before, item 4 = same path as 3
+    assert log.index(("gpu", 1)) < log.index(("saved", 0))                               # overlap: next item started first
+    cbs = [n for n, (k, _) in enumerate(log) if k == "cb"]
+    assert cbs[0] > log.index(("saved", 0))         # progress is reported once an item has really been written
+    assert cbs[1] > log.index(("saved", 1))
+    assert cbs[3] > log.index(("saved", 3)) and kinds[-1] == "cb"
+    assert all(os.path.exists(p) for p in paths)
