@@ -80,7 +80,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.dj_abi_version() != 1:
+        if L.dj_abi_version() != 2:
             raise RuntimeError("deepjoin_b200: ABI version mismatch")
         _lib = L
     return _lib

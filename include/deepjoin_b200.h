@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DJ_ABI_VERSION 1
+#define DJ_ABI_VERSION 2
 
 /* status codes */
 #define DJ_OK 0

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(L, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
-    assert _lib.lib().dj_abi_version() == 1
+    assert _lib.lib().dj_abi_version() == 2
 
 
 def test_status_codes_map_to_reference_exceptions():
