@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdeepjoin_b200.so")
 (OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SURFACE, ERR_LEVEL_RANGE, ERR_NO_SAMPLES, ERR_BAD_NET, ERR_DEVICE,
  ERR_PERMISSION, ERR_IO) = range(11)
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2}
+ABI_VERSION = 2  # == DJ_ABI_VERSION in include/deepjoin_b200.h (checked by tests/test_host_cpu.py)
 
 c_i, c_i64, c_d, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_float, ctypes.c_void_p
 
@@ -80,8 +81,9 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        if L.dj_abi_version() != 2:
-            raise RuntimeError("deepjoin_b200: ABI version mismatch")
+        got = L.dj_abi_version()
+        if got != ABI_VERSION:
+            raise RuntimeError("deepjoin_b200: ABI version mismatch: library %d, bindings %d (rebuild: python -m deepjoin_b200.build --force)" % (got, ABI_VERSION))
         _lib = L
     return _lib
 
