@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libdeepjoin_b200.so")
 
 (OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SURFACE, ERR_LEVEL_RANGE, ERR_NO_SAMPLES, ERR_BAD_NET, ERR_DEVICE,
  ERR_PERMISSION, ERR_IO) = range(11)
-PREC = {"fp32": 0, "bf16": 1, "fp16": 2}
+PREC = {"fp32": 0, "bf16": 1, "fp16": 2, "fp16x2": 3}
 ABI_VERSION = 2  # == DJ_ABI_VERSION in include/deepjoin_b200.h (checked by tests/test_host_cpu.py)
 
 c_i, c_i64, c_d, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_float, ctypes.c_void_p

@@ -35,6 +35,9 @@ struct DjPack {
   uint8_t* stream2[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   uint8_t* stream2h[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // the same stages with IEEE-half weights (DJ_PREC_FP16)
   tc2::Net nets2[2];
+  // split-operand program (DJ_PREC_FP16X2): every K = 128 stage twice (W_hi, W_lo; IEEE half, scaled per layer)
+  uint8_t* stream2x[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+  tc2::Net nets2x[2];
   unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
   // fused forward+backward program of the latent step (latent_tc2.cuh)
   uint8_t* lat_stream[2] = {nullptr, nullptr};
@@ -65,6 +68,8 @@ static void free_pack(DjPack* p) {
       if (p->stream2[i][r]) cudaFree(p->stream2[i][r]);
     for (int r = 0; r < 2; r++)
       if (p->stream2h[i][r]) cudaFree(p->stream2h[i][r]);
+    for (int r = 0; r < 2; r++)
+      if (p->stream2x[i][r]) cudaFree(p->stream2x[i][r]);
   }
   if (p->bias_dev) cudaFree(p->bias_dev);
   for (int r = 0; r < 2; r++) {
@@ -122,6 +127,44 @@ static void pack_tile_l0(const float* W, int ldw, int xyz_off, int n0, int rows,
         memcpy(dst + off, &b, 2);
       }
     }
+}
+
+// split-operand tiles (DJ_PREC_FP16X2): the weight times `scale` (a power of two) as IEEE half, part 0 = the rounded
+// value, part 1 = the rounding remainder (again rounded to half): hi + lo carries 22 significant bits
+static inline float half_part(float w, int part) {
+  const float hi = __half2float(__float2half_rn(w));
+  return part == 0 ? hi : __half2float(__float2half_rn(w - hi));
+}
+static void pack_tile_x2(const float* W, int ldw, int n_real, int k_real, int n0, int k0, int rows, uint8_t* dst, float scale, int part) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      const int gn = n0 + r, gk = k0 + k;
+      const float v = (gn < n_real && gk < k_real) ? W[(size_t)gn * ldw + gk] * scale : 0.f;
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      const __half b = __float2half_rn(half_part(v, part));
+      memcpy(dst + off, &b, 2);
+    }
+}
+// layer-0 tile of the split-operand program: [W_hi | W_hi | W_lo | 0] of the scaled xyz columns
+static void pack_tile_l0_x2(const float* W, int ldw, int xyz_off, int n0, int rows, uint8_t* dst, float scale) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      float v = 0.f;
+      if (k < 9) v = half_part(W[(size_t)(n0 + r) * ldw + xyz_off + k % 3] * scale, k < 6 ? 0 : 1);
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      const __half b = __float2half_rn(v);
+      memcpy(dst + off, &b, 2);
+    }
+}
+// power of two that brings the largest |w| of a layer into [256, 512): the low halves of all but vanishing weights
+// then stay normal numbers (IEEE half: 2^-14), and products with activations up to ~1e2 stay far inside fp32
+static float x2_scale(const float* W, size_t n) {
+  float m = 0.f;
+  for (size_t i = 0; i < n; i++) m = std::max(m, fabsf(W[i]));
+  if (!(m > 0.f) || !std::isfinite(m)) return 1.f;
+  int e = 0;
+  frexpf(m, &e);  // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, std::max(-24, std::min(24, 9 - e)));
 }
 
 // transposed source: tile row n, column k <- W[k0 + k][n0 + n]  (B operand of a backward GEMM, dX = dY . W)
@@ -285,7 +328,8 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     std::vector<uint8_t> blob[2], blobh[2];
     {
       tc2::Layer& T = N.layers[0];
-      T.n_chunks = 4; T.k_stages = 1; T.k_steps = 1; T.mma_n = 128; T.kind = tc2::KIND_L0TC;
+      T.n_chunks = 4; T.k_stages = 1; T.k_steps = 1; T.mma_n = 128; T.kind = tc2::KIND_L0TC; T.inv_scale = 1.f; T.k_ranges = 1;
+      T.korder[0] = T.korder[1] = 0x76543210u;
       T.tile_bytes = 64 * 128; T.stage_bytes = T.tile_bytes;
       const int xyz_off = (net == 0 ? L : Lb);
       for (int j = 0; j < 4; j++)
@@ -307,7 +351,10 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       if (T1.k_chunks % 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K chunks must be even", l));
       T.n_chunks = T1.n_chunks;
       T.k_stages = (int16_t)(T1.k_chunks / 2);
+      T.k_ranges = T.k_stages;
+      T.korder[0] = T.korder[1] = 0x76543210u;
       T.k_steps = 8;
+      T.inv_scale = 1.f;
       T.mma_n = (int16_t)(head ? 32 : 128);
       T.kind = T1.kind;
       T.bias_off = T1.bias_off;
@@ -332,6 +379,65 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       DJ_TRY(cudaMalloc((void**)&p->stream2h[net][r], blobh[r].size()));
       DJ_TRY(cudaMemcpy(p->stream2h[net][r], blobh[r].data(), blobh[r].size(), cudaMemcpyHostToDevice));
       N.stream[r] = p->stream2[net][r];
+    }
+  }
+  // ---- split-operand program: the pair program with every stage doubled (W_hi, W_lo) and per-layer scales
+  for (int net = 0; net < 2; net++) {
+    const int nl = net == 0 ? d->f_layers : d->h_layers;
+    const float* const* W = net == 0 ? f_w : h_w;
+    const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
+    const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
+    tc2::Net& N = p->nets2x[net];
+    N = p->nets2[net];
+    std::vector<uint8_t> blob[2];
+    {
+      tc2::Layer& T = N.layers[0];
+      const float sc = x2_scale(W[0], (size_t)outs[0] * ins[0]);
+      T.inv_scale = 1.f / sc;
+      const int xyz_off = (net == 0 ? L : Lb);
+      for (int j = 0; j < 4; j++)
+        for (int r = 0; r < 2; r++) {
+          const size_t o = blob[r].size();
+          blob[r].resize(o + T.tile_bytes);
+          pack_tile_l0_x2(W[0], ins[0], xyz_off, j * 128 + r * 64, 64, blob[r].data() + o, sc);
+        }
+    }
+    for (int l = 1; l < nl; l++) {
+      tc2::Layer& T = N.layers[l];
+      const bool reinj = (net == 0 && l == li);
+      const int n_real = outs[l];
+      const int k_real = reinj ? K3 : ins[l];
+      const float sc = x2_scale(W[l], (size_t)outs[l] * ins[l]);
+      T.inv_scale = 1.f / sc;
+      const int k_ranges = T.k_ranges;
+      T.k_stages = (int16_t)(2 * k_ranges);
+      const int rows = T.mma_n / 2;
+      // stage order of a chunk as (part, K range): W_lo stages before W_hi stages (mlp_tc2.cuh); chunk 0 defers its
+      // last K range, the one the previous layer's drain publishes last
+      std::vector<std::pair<int, int>> order[2];
+      for (int st = 0; st + 1 < k_ranges; st++) order[0].push_back({1, st});
+      for (int st = 0; st + 1 < k_ranges; st++) order[0].push_back({0, st});
+      order[0].push_back({1, k_ranges - 1});
+      order[0].push_back({0, k_ranges - 1});
+      for (int part = 1; part >= 0; part--)
+        for (int st = 0; st < k_ranges; st++) order[1].push_back({part, st});
+      for (int c = 0; c < 2; c++) {
+        T.korder[c] = 0;
+        for (size_t i = 0; i < order[c].size(); i++) T.korder[c] |= (uint32_t)order[c][i].second << (4 * i);
+      }
+      for (int j = 0; j < T.n_chunks; j++)
+        for (const auto& ps : order[j == 0 ? 0 : 1])
+          for (int r = 0; r < 2; r++)
+            for (int kc = 0; kc < 2; kc++) {
+              const size_t o = blob[r].size();
+              blob[r].resize(o + T.tile_bytes);
+              pack_tile_x2(W[l], ins[l], n_real, k_real, j * T.mma_n + r * rows, (2 * ps.second + kc) * 64, rows, blob[r].data() + o, sc, ps.first);
+            }
+    }
+    for (int r = 0; r < 2; r++) {
+      DJ_TRY(cudaMalloc((void**)&p->stream2x[net][r], blob[r].size()));
+      DJ_TRY(cudaMemcpy(p->stream2x[net][r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
+      N.stream[r] = p->stream2x[net][r];
     }
   }
   // ---- latent-step program (latent_tc2.cuh): forward, loss, backward in one pass over the tile
@@ -515,12 +621,13 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
   if (n <= 0) return DJ_OK;
   int rc;
   if (do_fold && (rc = launch_fold(p, code_dev, st))) return rc;
-  if (precision == DJ_PREC_BF16 || precision == DJ_PREC_FP16) {
+  if (precision == DJ_PREC_BF16 || precision == DJ_PREC_FP16 || precision == DJ_PREC_FP16X2) {
     const bool f16 = precision == DJ_PREC_FP16;
+    const bool x2 = precision == DJ_PREC_FP16X2;
     tc2::Params P;
     memset(&P, 0, sizeof P);
-    P.nets[0] = p->nets2[0];
-    P.nets[1] = p->nets2[1];
+    P.nets[0] = x2 ? p->nets2x[0] : p->nets2[0];
+    P.nets[1] = x2 ? p->nets2x[1] : p->nets2[1];
     if (f16)
       for (int net = 0; net < 2; net++)
         for (int r = 0; r < 2; r++) P.nets[net].stream[r] = p->stream2h[net][r];
@@ -538,15 +645,18 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     P.out = out_dev;
     P.err = p->err;
     P.prof = p->prof;
-    const int64_t ntiles = (n + tc2::TILE_M - 1) / tc2::TILE_M;
+    const int tile_pts = x2 ? tc2::TILE_PTS_X2 : tc2::TILE_M;
+    const int64_t ntiles = (n + tile_pts - 1) / tile_pts;
     const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);  // whole CTA pairs
     if (!p->tc_attr_set2) {
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       p->tc_attr_set2 = true;
     }
-    if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    if (x2) tc2::tc2_forward_kernel<0, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    else if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else if (P.debug) tc2::tc2_forward_kernel<1, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else tc2::tc2_forward_kernel<0, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     DJ_LAUNCHED();
@@ -875,7 +985,7 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
   memset(&P, 0, sizeof P);
   memcpy(P.prog, p->lat_prog, sizeof(lat2::Layer) * p->lat_n_prog);
   P.n_prog = p->lat_n_prog;
-  const bool half_fwd = cfg->precision == DJ_PREC_FP16;  // forward in IEEE half (8x finer than bf16: the loss gates follow
+  const bool half_fwd = cfg->precision == DJ_PREC_FP16 || cfg->precision == DJ_PREC_FP16X2;  // forward in IEEE half (8x finer than bf16: the loss gates follow
                                                          // the fp32 forward far more often); backward always bf16 (range)
   P.stream[0] = half_fwd ? p->lat_stream_h[0] : p->lat_stream[0];
   P.stream[1] = half_fwd ? p->lat_stream_h[1] : p->lat_stream[1];
@@ -911,7 +1021,7 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
 
 static int check_latent_cfg(DjPack* p, const DjLatentCfg* cfg) {
   if (!cfg) return fail(DJ_ERR_INVALID, "null DjLatentCfg");
-  if (cfg->precision != DJ_PREC_FP32 && cfg->precision != DJ_PREC_BF16 && cfg->precision != DJ_PREC_FP16)
+  if (cfg->precision != DJ_PREC_FP32 && cfg->precision != DJ_PREC_BF16 && cfg->precision != DJ_PREC_FP16 && cfg->precision != DJ_PREC_FP16X2)
     return fail(DJ_ERR_INVALID, "latent gradient: unknown precision %d", cfg->precision);
   if (p->L + p->Lb > 256) return fail(DJ_ERR_UNSUPPORTED, "code length > 256");
   if (cfg->loss_kind != DJ_LOSS_DEEPJOIN && cfg->loss_kind != DJ_LOSS_DEEPSDF)

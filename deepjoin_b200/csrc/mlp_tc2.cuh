@@ -51,6 +51,12 @@ constexpr int SM_BAR = SM_TAB + 512 * 16;
 constexpr int SM_END = SM_BAR + 256;
 constexpr int SMEM_BYTES = SM_END + 1024;  // slack for 1024-B alignment
 
+// split-operand mode (X2): the ring has 4 stages and the fifth slot is the exchange buffer between the warp that
+// drains TMEM lanes [0,64) (high halves) and the one that drains lanes [64,128) (low halves) of the same points
+constexpr int NSTAGES_X2 = 4;
+constexpr int SM_X = SM_W + NSTAGES_X2 * STAGE_BYTES;  // 16 KB: 4 warp pairs x 32 lanes x 32 words
+constexpr int TILE_PTS_X2 = 64;
+
 constexpr uint32_t TM_A = 0;      // TMEM columns [0,256): bf16 activations (A operand of odd layers)
 constexpr uint32_t TM_ACC = 256;  // TMEM columns [256,512): two fp32 accumulator buffers
 
@@ -64,6 +70,11 @@ struct Layer {
   int32_t stage_bytes;  // per CTA
   int32_t tile_bytes;   // one [mma_n/2 x 64] tile
   int32_t k_steps;      // MMAs per ring stage: 8 (K = 128), or 1 for the K = 16 operand of layer 0
+  int16_t k_ranges;     // K / 128 of the activations (k_stages = k_ranges, or 2 k_ranges in split-operand mode)
+  int16_t pad;
+  uint32_t korder[2];   // nibble s = K range ring stage s of a chunk reads; [0]: chunk 0, [1]: the other chunks
+  float inv_scale;      // split-operand mode: the weights of this layer are stored times a power of two (so that the
+                        // low halves stay normal IEEE-half numbers); the drain multiplies the accumulator by this
 };
 constexpr int KIND_L0TC = 3;  // layer 0 on the tensor core: xyz split hi/lo into a K = 16 operand, drained like KIND_HIDDEN
 struct Net {
@@ -106,7 +117,26 @@ __device__ __forceinline__ void grid_point(const Params& P, int64_t r, float& x,
 // DBG = 1 compiles the bench diagnostics in (Params::debug knobs and cycle counters); the product path
 // launches DBG = 0.
 // F16 = 1: IEEE-half operands (DJ_PREC_FP16) instead of bf16 -- same instruction, same speed, 8x finer rounding.
-template <int DBG, int F16>
+// X2 = 1 (with F16 = 1): split-operand mode, DJ_PREC_FP16X2.  Every activation a and weight W is carried as a
+// high + low IEEE-half pair (22 significant bits) and ALL FOUR partial products are accumulated in fp32:
+//   * a CTA owns 64 points; row m < 64 of its A operand holds a_hi of point m, row m + 64 holds a_lo of the same
+//     point, so one 256 x 128 x 16 MMA of the pair multiplies both halves with a weight tile;
+//   * the weight stream carries the K = 128 stages of a chunk twice, all of W_lo and then all of W_hi (scaled by a
+//     power of two per layer so that W_lo stays a normal half), accumulating into the same TMEM columns: lanes
+//     [0,64) end up with a_hi.W, lanes [64,128) with a_lo.W.  W_lo goes first because the tensor core truncates
+//     (rounds toward zero) whatever it adds to the accumulator at the accumulator's exponent, ~0.46 ulp per MMA
+//     (tools/probe_rounding.py): the small a.W_lo terms are summed while the accumulator is still small.  Chunk 0 of
+//     a layer takes its LAST K range after everything else (W_lo, W_hi of the other ranges, then W_lo, W_hi of the
+//     last): that range is published by the drain of the previous layer's last chunk, which the MMAs of the
+//     other ranges hide;
+//   * the drain adds the two (the low-half warp hands its 64 columns to the high-half warp through shared memory,
+//     as bf16 pairs: it is a 2^-11 correction), applies scale / bias / LeakyReLU in fp32 and splits the result
+//     into the next layer's a_hi / a_lo rows.
+// 4x the MMA work of the single-pass kernel per point (the a_lo.W_lo quarter is not needed but cannot be
+// skipped: both halves of a point ride in the same MMA), error ~1e-5 of fp64 on trained-norm weights, where single
+// pass bf16 has 5e-2 and IEEE half 8e-3.  A 3-pass K-stacked variant would need a_hi and a_lo of 128 points per CTA
+// on chip (2 x 128 KB per buffer, x2 for the ping-pong): it does not fit next to the accumulators.
+template <int DBG, int F16, int X2 = 0>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_forward_kernel(const __grid_constant__ Params P) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -125,9 +155,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 12));
   static_assert(8 * (2 * NSTAGES + 12) + 4 <= 256, "barrier block");
 
+  constexpr int NST = X2 ? NSTAGES_X2 : NSTAGES;          // ring depth
+  constexpr int TILE_PTS = X2 ? TILE_PTS_X2 : TILE_M;    // points per CTA and pass
+  const uint32_t sX = base + SM_X;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
-  const int64_t ntiles = (P.n + TILE_M - 1) / TILE_M;
+  const int64_t ntiles = (P.n + TILE_PTS - 1) / TILE_PTS;
   // both CTAs of a pair (and, for simplicity, all pairs) run the same number of passes; passes beyond
   // the last tile compute on zeros and write nothing
   const int64_t iters = (ntiles + gridDim.x - 1) / gridDim.x;
@@ -139,7 +172,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
   const long long t_begin = tick();
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < NSTAGES; s++) {
+    for (int s = 0; s < NST; s++) {
       ptx::mbar_init(W_FULL(s), rank == 0 ? 2 : 1);  // leader: own copy + the peer's relay
       ptx::mbar_init(W_EMPTY(s), 1);
     }
@@ -181,7 +214,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             }
             __syncwarp();
             src += bytes;
-            if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+            if (++stage == NST) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -200,7 +233,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       { const long long t = tick(); ptx::mbar_spin(W_FULL(stage), phase); w0 += tick() - t; }
       if (ptx::elect_one()) ptx::mbar_arrive_cluster(lead_full0 + 8u * stage);
       __syncwarp();
-      if (++stage == NSTAGES) { stage = 0; phase ^= 1; }
+      if (++stage == NST) { stage = 0; phase ^= 1; }
     }
     if (prof && lane == 0) { pc[11] = tick() - t_begin; pc[12] = w0; }
   } else if (warp == 1) {
@@ -224,11 +257,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
         const int nl = N.n_layers;
         for (int l = 0; l < nl; l++) {
           const int n_chunks = N.layers[l].n_chunks, k_stages = N.layers[l].k_stages, k_steps = N.layers[l].k_steps;
+          const int k_ranges = N.layers[l].k_ranges;
+          const uint32_t korder0 = N.layers[l].korder[0], korder1 = N.layers[l].korder[1];
           const uint32_t idesc = F16 ? ptx::umma_idesc_f16(256, (uint32_t)N.layers[l].mma_n) : ptx::umma_idesc_bf16(256, (uint32_t)N.layers[l].mma_n);
           const uint32_t tile16 = (uint32_t)N.layers[l].tile_bytes >> 4;
           const int src = l & 1;
           for (int j = 0; j < n_chunks; j++) {
             const uint32_t buf = acc_it & 1u;
+            const uint32_t korder = j == 0 ? korder0 : korder1;
             { const long long t = tick(); ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u); w1 += tick() - t; }
             acc_it++;
             const uint32_t d_tmem = tmem_base + TM_ACC + buf * NCH;
@@ -240,8 +276,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                 ptx::mma2_f16_ss(d_tmem, a_desc0, bd, idesc, 0u);
                 return;
               }
+              const int ak = (int)((korder >> (4 * sidx)) & 15u);  // K range [128 ak, 128 ak + 128) of the activations
               if (src == 0) {
-                const uint64_t ad = a_desc0 + (uint64_t)(sidx * 2 * (A_CHUNK_BYTES >> 4));
+                const uint64_t ad = a_desc0 + (uint64_t)(ak * 2 * (A_CHUNK_BYTES >> 4));
 #pragma unroll
                 for (int kc = 0; kc < 2; kc++)
 #pragma unroll
@@ -249,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                     ptx::mma2_f16_ss(d_tmem, ad + (uint64_t)(kc * (A_CHUNK_BYTES >> 4) + 2 * k), bd + (uint64_t)(kc * tile16 + 2 * k), idesc,
                                      (uint32_t)((sidx | kc | k) != 0));
               } else {
-                const uint32_t at = tmem_base + TM_A + (uint32_t)(sidx * KCH);
+                const uint32_t at = tmem_base + TM_A + (uint32_t)(ak * KCH);
 #pragma unroll
                 for (int kc = 0; kc < 2; kc++)
 #pragma unroll
@@ -263,20 +300,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             while (sidx < k_stages) {
               const bool two = sidx + 1 < k_stages;
               const uint32_t st0 = stage, ph0 = phase;
-              const uint32_t st1 = (st0 + 1 == NSTAGES) ? 0u : st0 + 1, ph1 = ph0 ^ (uint32_t)(st1 == 0);
+              const uint32_t st1 = (st0 + 1 == NST) ? 0u : st0 + 1, ph1 = ph0 ^ (uint32_t)(st1 == 0);
               if (j == 0) {
                 const long long t = tick();
-                ptx::mbar_spin_cluster(A_READY(src, sidx), (a_ph >> (4 * src + sidx)) & 1u);
-                if (two) ptx::mbar_spin_cluster(A_READY(src, sidx + 1), (a_ph >> (4 * src + sidx + 1)) & 1u);
+                const int ak0 = (int)((korder >> (4 * sidx)) & 15u), ak1 = (int)((korder >> (4 * sidx + 4)) & 15u);
+                ptx::mbar_spin_cluster(A_READY(src, ak0), (a_ph >> (4 * src + ak0)) & 1u);
+                if (two && ak1 != ak0) ptx::mbar_spin_cluster(A_READY(src, ak1), (a_ph >> (4 * src + ak1)) & 1u);
                 w2 += tick() - t;
               }
               if (!ok0) { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(st0), ph0); w3 += tick() - t; }
               if (two && !ok1) { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(st1), ph1); w3 += tick() - t; }
               ptx::tc_fence_after();
               // probe the coming trip's barriers now: the polls' latency hides behind the MMA issue below
-              const uint32_t nst0 = two ? ((st1 + 1 == NSTAGES) ? 0u : st1 + 1) : st1;
+              const uint32_t nst0 = two ? ((st1 + 1 == NST) ? 0u : st1 + 1) : st1;
               const uint32_t nph0 = two ? (ph1 ^ (uint32_t)(nst0 == 0)) : ph1;
-              const uint32_t nst1 = (nst0 + 1 == NSTAGES) ? 0u : nst0 + 1, nph1 = nph0 ^ (uint32_t)(nst1 == 0);
+              const uint32_t nst1 = (nst0 + 1 == NST) ? 0u : nst0 + 1, nph1 = nph0 ^ (uint32_t)(nst1 == 0);
               ok0 = ptx::mbar_test(W_FULL(nst0), nph0);
               ok1 = ptx::mbar_test(W_FULL(nst1), nph1);
               if (ptx::elect_one()) {
@@ -293,13 +331,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
               phase = nph0;
               sidx += two ? 2 : 1;
             }
-            if (j == 0) a_ph ^= ((1u << k_stages) - 1u) << (4 * src);
+            if (j == 0) a_ph ^= ((1u << k_ranges) - 1u) << (4 * src);
           }
         }
       }
     }
     if (prof && lane == 0) { pc[0] = tick() - t_begin; pc[1] = w1; pc[2] = w2; pc[3] = w3; }
-  } else {
+  } else if constexpr (X2 == 0) {
     // ===================== epilogue: 8 warps; thread = (row, 64-column half of the chunk) ==========
     const int q = warp & 3;              // TMEM lane quarter this warp may access
     const int h = (warp - 2) >> 2;       // columns [64 h, 64 h + 64) of every 128-column chunk
@@ -478,6 +516,253 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       if (h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
     }
     if (prof && warp == 2 && lane == 0) { pc[4] = tick() - t_begin; pc[5] = w0; pc[6] = w1; pc[7] = w2; pc[8] = w3; }
+  } else {
+    // ===================== epilogue, split-operand mode (X2) ==========
+    // TMEM lane quarter q = warp % 4: quarters 0, 1 hold the a_hi rows of the tile's 64 points ("high" warps),
+    // quarters 2, 3 the a_lo rows of the same points ("low" warps).  High warp (q, h) and low warp (q + 2, h) drain
+    // the same 64 columns of the same 32 points and form a pair with a 4 KB exchange slot and three named barriers:
+    //   B_FULL: low -> high, "my partial sums are in the slot";  B_FREE: high -> low, "the slot may be rewritten";
+    //   B_BACK: high -> low, "the a_lo words you have to put into your TMEM lanes are in the slot".
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const bool lo_warp = q >= 2;
+    const int prow = (q & 1) * 32 + lane;  // point of the tile, 0..63
+    const int row = q * 32 + lane;         // operand row / TMEM lane of this thread: prow (a_hi) or prow + 64 (a_lo)
+    const int et = threadIdx.x - 64;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_row = sA + prow * 128;  // a_hi row; the a_lo row of the same point is 64 rows = 8192 B further
+    const int sw = prow & 7;
+    const uint32_t pair = (uint32_t)((q & 1) * 2 + h);
+    const uint32_t xs = sX + pair * 4096u + (uint32_t)lane * 16u;  // 16-byte granule g of this lane at xs + 512 g
+    const uint32_t B_FULL = 2u + pair, B_FREE = 6u + pair, B_BACK = 10u + pair;
+    const float slope = P.head.slope;
+    const uint64_t slope2 = ptx::pack_f32x2(slope, slope);
+    const uint32_t lead_aready0 = ptx::mapa(A_READY(0, 0), 0);
+    const uint32_t lead_accempty0 = ptx::mapa(ACC_EMPTY(0), 0);
+    uint32_t acc_it = 0;
+    int bias_buf = 0;
+    if (!lo_warp) ptx::bar_arrive_n(B_FREE, 64);  // the slot starts out free
+
+    for (int64_t it = 0; it < iters; it++) {
+      const int64_t tile = it * gridDim.x + blockIdx.x;
+      const int64_t g = tile * TILE_PTS + prow;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (!lo_warp && g < P.n) {
+        if (P.grid_mode) grid_point(P, P.r_lo + g, x, y, z);
+        else { x = __ldg(P.xyz + 3 * g); y = __ldg(P.xyz + 3 * g + 1); z = __ldg(P.xyz + 3 * g + 2); }
+      }
+      float yc[5] = {0, 0, 0, 0, 0}, yt[5] = {0, 0, 0, 0, 0};
+
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const Net& N = P.nets[net];
+        // ---- layer 0: K = 16 operand [p_hi | p_lo | p_hi | 0] in the point's a_hi row (the tiles hold
+        // [W_hi | W_hi | W_lo]: three of the four partial products, the fourth is below 2^-22); zeros in the a_lo row
+        tc::epi_bar();  // everybody is past the previous use of sBias
+        {
+          const float4* t = P.tables + N.l0_table * 512;
+          reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = make_float2(__ldg(&t[2 * et].w), __ldg(&t[2 * et + 1].w));
+        }
+        if (h == 0) {
+          uint32_t w[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+          if (!lo_warp) {
+            float hi[3], lo[3];
+            const float p3[3] = {x, y, z};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              hi[i] = ptx::round_op16<1>(p3[i]);
+              lo[i] = p3[i] - hi[i];
+            }
+            const float k[16] = {hi[0], hi[1], hi[2], lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = ptx::pack_op16x2<1>(k[2 * i], k[2 * i + 1]);
+          }
+          const uint32_t my_row = sA + row * 128;
+          tc::st_shared_v4(my_row + ((0 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+          tc::st_shared_v4(my_row + ((1 ^ sw) << 4), w[4], w[5], w[6], w[7]);
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0);  // A_READY(shared memory, K range 0)
+
+        for (int l = 0; l < N.n_layers; l++) {
+          const Layer L = N.layers[l];
+          const float inv = L.inv_scale;
+          if (L.kind == KIND_HEAD) {
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l);
+            acc_it++;
+            ptx::tc_fence_after();
+            uint32_t r[8];
+            if (h == 0) {
+              ptx::tmem_ld8(tmem_lane + TM_ACC + buf * NCH, r);
+              ptx::tmem_wait_ld();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
+            if (lo_warp) {
+              ptx::bar_sync_n(B_FREE, 64);
+              if (h == 0) {
+                ptx::st_shared_v4u(xs, r[0], r[1], r[2], r[3]);
+                ptx::st_shared_v4u(xs + 512, r[4], r[5], r[6], r[7]);
+              }
+              __threadfence_block();
+              ptx::bar_arrive_n(B_FULL, 64);
+            } else {
+              ptx::bar_sync_n(B_FULL, 64);
+              if (h == 0) {
+                uint32_t s[8];
+                ptx::ld_shared_v4u(xs, s[0], s[1], s[2], s[3]);
+                ptx::ld_shared_v4u(xs + 512, s[4], s[5], s[6], s[7]);
+                float* dst = net == 0 ? yc : yt;
+#pragma unroll
+                for (int i = 0; i < 5; i++) {
+                  const float v = fmaf(__uint_as_float(r[i]) + __uint_as_float(s[i]), inv, __ldg(P.bias + L.bias_off + i));
+                  dst[i] = N.head_leaky ? tc::leaky(v, slope) : v;
+                }
+              }
+              ptx::bar_arrive_n(B_FREE, 64);
+            }
+            continue;
+          }
+          const int dsti = (l + 1) & 1;
+          tc::epi_bar();
+          const int next_kind = (l + 1 < N.n_layers) ? N.layers[l + 1].kind : -1;
+          float2 pre_b = make_float2(0.f, 0.f);
+          float4 pre_t0 = make_float4(0, 0, 0, 0), pre_t1 = pre_t0;
+          if (next_kind == KIND_HIDDEN) {
+            pre_b = __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[l + 1].bias_off) + et);
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            const float4* t = P.tables + N.layers[l + 1].table * 512;
+            pre_t0 = __ldg(t + et);
+            pre_t1 = __ldg(t + et + 256);
+          }
+          const float* bias = sBias + bias_buf * 512;
+          const uint64_t inv2 = ptx::pack_f32x2(inv, inv);
+
+          auto drain = [&](auto kind_c, auto dst_c, int j) {
+            constexpr int KIND = decltype(kind_c)::value;
+            constexpr int DST = decltype(dst_c)::value;
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j);
+            acc_it++;
+            ptx::tc_fence_after();
+            uint32_t r[64];
+            ptx::tmem_ld64(tmem_lane + TM_ACC + buf * NCH + h * 64, r);
+            ptx::tmem_wait_ld();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);  // accumulator buffer is free again
+            const int col0 = j * NCH + h * 64;
+            const int c = 2 * j + h;  // 64-wide K chunk of the next layer this warp pair produces
+            if (lo_warp) {
+              // a_lo . W of my 64 columns -> bf16 pairs -> the pair's slot
+              ptx::bar_sync_n(B_FREE, 64);
+#pragma unroll
+              for (int gq = 0; gq < 8; gq++) {
+                uint32_t w[4];
+#pragma unroll
+                for (int f = 0; f < 4; f++)
+                  w[f] = ptx::pack_bf16x2(__uint_as_float(r[gq * 8 + 2 * f]), __uint_as_float(r[gq * 8 + 2 * f + 1]));
+                ptx::st_shared_v4u(xs + 512 * gq, w[0], w[1], w[2], w[3]);
+              }
+              __threadfence_block();
+              ptx::bar_arrive_n(B_FULL, 64);
+              if (DST == 1) {
+                // the a_lo halves of the next layer's operand belong in MY TMEM lanes: the high warp hands them back
+                ptx::bar_sync_n(B_BACK, 64);
+                uint32_t pk[32];
+#pragma unroll
+                for (int gq = 0; gq < 8; gq++)
+                  ptx::ld_shared_v4u(xs + 512 * gq, pk[gq * 4], pk[gq * 4 + 1], pk[gq * 4 + 2], pk[gq * 4 + 3]);
+                ptx::tmem_st32(tmem_lane + TM_A + (uint32_t)(c * (KCH / 2)), pk);
+                ptx::tmem_wait_st();
+                ptx::tc_fence_before();
+              }
+            } else {
+              ptx::bar_sync_n(B_FULL, 64);
+              uint32_t pkh[32];
+#pragma unroll
+              for (int gq = 0; gq < 8; gq++) {
+                uint32_t w[4], pl[4];
+                ptx::ld_shared_v4u(xs + 512 * gq, w[0], w[1], w[2], w[3]);
+                float v[8];
+                if (KIND == KIND_HIDDEN_XYZ) {
+#pragma unroll
+                  for (int f = 0; f < 4; f++) {
+                    const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                    const uint64_t t = ptx::add_f32x2(acc, ptx::bf16x2_to_f32x2(w[f]));
+                    const float4 t0 = sTab[col0 + gq * 8 + 2 * f], t1 = sTab[col0 + gq * 8 + 2 * f + 1];
+                    const float s0 = fmaf(t0.x, x, fmaf(t0.y, y, fmaf(t0.z, z, t0.w)));
+                    const float s1 = fmaf(t1.x, x, fmaf(t1.y, y, fmaf(t1.z, z, t1.w)));
+                    v[2 * f] = tc::leaky(fmaf(ptx::f32x2_lo(t), inv, s0), slope);
+                    v[2 * f + 1] = tc::leaky(fmaf(ptx::f32x2_hi(t), inv, s1), slope);
+                  }
+                } else {
+                  const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
+                  const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8 + 4);
+                  const uint64_t bb[4] = {ptx::pack_f32x2(b0.x, b0.y), ptx::pack_f32x2(b0.z, b0.w),
+                                          ptx::pack_f32x2(b1.x, b1.y), ptx::pack_f32x2(b1.z, b1.w)};
+#pragma unroll
+                  for (int f = 0; f < 4; f++) {
+                    const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                    const uint64_t t = ptx::fma_f32x2(ptx::add_f32x2(acc, ptx::bf16x2_to_f32x2(w[f])), inv2, bb[f]);
+                    const uint64_t u = ptx::mul_f32x2(t, slope2);
+                    v[2 * f] = fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u));
+                    v[2 * f + 1] = fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u));
+                  }
+                }
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                  const uint32_t ph = ptx::pack_f16x2(v[2 * f], v[2 * f + 1]);
+                  const float2 back = ptx::f16x2_to_float2(ph);
+                  pkh[gq * 4 + f] = ph;
+                  pl[f] = ptx::pack_f16x2(v[2 * f] - back.x, v[2 * f + 1] - back.y);
+                }
+                if (DST == 0) {
+                  const uint32_t dsta = a_row + c * A_CHUNK_BYTES + ((gq ^ sw) << 4);
+                  tc::st_shared_v4(dsta, pkh[gq * 4], pkh[gq * 4 + 1], pkh[gq * 4 + 2], pkh[gq * 4 + 3]);
+                  tc::st_shared_v4(dsta + 64 * 128, pl[0], pl[1], pl[2], pl[3]);
+                } else {
+                  ptx::st_shared_v4u(xs + 512 * gq, pl[0], pl[1], pl[2], pl[3]);  // read above by this same thread
+                }
+              }
+              if (DST == 0) {
+                ptx::fence_proxy_async_smem();
+              } else {
+                __threadfence_block();
+                ptx::bar_arrive_n(B_BACK, 64);
+                ptx::tmem_st32(tmem_lane + TM_A + (uint32_t)(c * (KCH / 2)), pkh);
+                ptx::tmem_wait_st();
+                ptx::tc_fence_before();
+              }
+              ptx::bar_arrive_n(B_FREE, 64);
+            }
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * (4 * DST + j));
+          };
+          using I0 = std::integral_constant<int, 0>;
+          using I1 = std::integral_constant<int, 1>;
+          if (L.kind == KIND_HIDDEN_XYZ) {
+            if (dsti) for (int j = 0; j < L.n_chunks; j++) drain(I1{}, I1{}, j);
+            else for (int j = 0; j < L.n_chunks; j++) drain(I1{}, I0{}, j);
+          } else {
+            if (dsti) for (int j = 0; j < L.n_chunks; j++) drain(I0{}, I1{}, j);
+            else for (int j = 0; j < L.n_chunks; j++) drain(I0{}, I0{}, j);
+          }
+          if (next_kind == KIND_HIDDEN) {
+            bias_buf ^= 1;
+            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = pre_b;
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            sTab[et] = pre_t0;
+            sTab[et + 256] = pre_t1;
+          }
+        }
+      }
+      if (!lo_warp && h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
+    }
+    if (lo_warp) ptx::bar_sync_n(B_FREE, 64);  // consume the last hand-back so that no barrier is left half-arrived
   }
 
   ptx::tc_fence_before();

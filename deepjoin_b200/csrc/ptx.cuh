@@ -377,5 +377,30 @@ __device__ __forceinline__ uint32_t pack_op16x2<0>(float lo, float hi) { return 
 template <>
 __device__ __forceinline__ uint32_t pack_op16x2<1>(float lo, float hi) { return pack_f16x2(lo, hi); }
 
+
+// ---------------------------------------------------------------- named barriers / plain shared-memory access
+// producer / consumer hand-off between two warps: the producer arrives (does not wait), the consumer syncs
+__device__ __forceinline__ void bar_sync_n(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void bar_arrive_n(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4u(uint32_t dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4u(uint32_t src, uint32_t& a, uint32_t& b, uint32_t& c, uint32_t& d) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(b), "=r"(c), "=r"(d) : "r"(src) : "memory");
+}
+// the two floats of a packed bf16x2 word, as an f32x2 pair (low half -> low float)
+__device__ __forceinline__ uint64_t bf16x2_to_f32x2(uint32_t w) {
+  return (uint64_t)(w << 16) | ((uint64_t)(w & 0xFFFF0000u) << 32);
+}
+__device__ __forceinline__ float2 f16x2_to_float2(uint32_t w) {
+  __half2 h;
+  memcpy(&h, &w, 4);
+  return __half22float2(h);
+}
+
 }  // namespace ptx
 }  // namespace dj

@@ -54,7 +54,7 @@ class Decoder(nn.Module):
             out_dim = dims[layer + 1] - dims[0] if (layer + 1) in latent_in else dims[layer + 1]
             wn = weight_norm and (layer in (norm_layers or ()))
             setattr(self, "lin%d" % layer, (_WNLinear if wn else _Linear)(dims[layer], out_dim))
-        self.precision = os.environ.get("DEEPJOIN_B200_PRECISION", "bf16")
+        self.precision = os.environ.get("DEEPJOIN_B200_PRECISION", "fp16x2")
         # latent optimisation (reconstruct_deepsdf.reconstruct): the baseline's objective is a sign-gated L1, so a
         # forward rounding error flips whole per-sample gradients; IEEE-half forward operands (8x finer than bf16)
         # keep the tensor-core gradient within ~1e-2 of fp32 even at small batches

@@ -101,7 +101,7 @@ class Decoder(nn.Module):
             wn = weight_norm and (layer in (norm_layers or ()))
             setattr(self, "lin%d" % layer, (_WNLinear if wn else _Linear)(dims[layer], out_dim))
 
-        self.precision = os.environ.get("DEEPJOIN_B200_PRECISION", "bf16")
+        self.precision = os.environ.get("DEEPJOIN_B200_PRECISION", "fp16x2")
         self._pack = None
         self._pack_key = None
 

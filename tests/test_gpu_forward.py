@@ -1,8 +1,10 @@
-"""GPU parity of the decoder forward (fp32 CUDA-core path and bf16 tcgen05 path) against the
-oracle restatement and the golden vectors produced by the reference itself.
+"""GPU parity of the decoder forward (fp32 CUDA-core path, split-operand and single-pass tcgen05 paths) against
+the oracle restatement and the golden vectors produced by the reference itself.
 
-Tolerances (BASELINE.json north_star): SDF 1e-3, normals / occupancy probability 1e-2 for the
-fp32-accumulated bf16 path; the fp32 path is held to fp32 round-off."""
+Tolerances (BASELINE.json north_star): SDF 1e-3, normals / occupancy probability 1e-2.  The split-operand
+tensor-core mode ("fp16x2", the default precision) and the fp32 path are held 10x tighter than that on BOTH weight
+sets; single-pass bf16 meets it only on default-init weights and is held to its measured budget on trained-norm
+weights (it is the opt-in throughput mode)."""
 import os
 
 import numpy as np
@@ -16,18 +18,19 @@ from tests import util
 pytestmark = pytest.mark.gpu
 G = util.GOLDEN
 NAMES = ("c_occ", "b_occ", "r_occ", "t_occ", "c_sdf", "b_sdf", "r_sdf", "t_sdf", "c_n", "b_n", "r_n", "t_n")
-SDF_TOL = {"fp32": 2e-5, "bf16": 1e-3}
-PROB_TOL = {"fp32": 2e-5, "bf16": 1e-2}
+SDF_TOL = {"fp32": 2e-5, "fp16x2": 2e-5, "bf16": 1e-3}
+PROB_TOL = {"fp32": 2e-5, "fp16x2": 2e-5, "bf16": 1e-2}
+NORTH_STAR_SDF, NORTH_STAR_PROB = 1e-3, 1e-2
 
 
 def _tols(precision, kind):
-    # trained-norm weights amplify rounding: bf16 is reported, fp32 stays tight
-    if kind == "trained_norm" and precision == "fp32":
+    # trained-norm weights amplify rounding: bf16 is reported, fp32 / fp16x2 stay tight
+    if kind == "trained_norm" and precision in ("fp32", "fp16x2"):
         return 2e-4, 2e-4
     return SDF_TOL[precision], PROB_TOL[precision]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2", "bf16"])
 @pytest.mark.parametrize("seed", [0, 1])
 def test_default_weights_all_branches_vs_golden(precision, seed):
     g = np.load(os.path.join(G, "decoder_forward.npz"))
@@ -52,11 +55,13 @@ def test_default_weights_all_branches_vs_golden(precision, seed):
         assert np.abs(o - g[tag + "_u%d_occ" % u]).max() <= pt, u
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
 @pytest.mark.parametrize("seed", [0, 1])
-def test_trained_norm_weights_fp32_vs_golden(seed):
+def test_trained_norm_weights_vs_golden(seed, precision):
+    """The reference's own outputs (fp32 torch, tests/golden/make_golden.py) on weights with the trained norms."""
     g = np.load(os.path.join(G, "decoder_forward.npz"))
     tag = "trained_norm_s%d" % seed
-    dec = util.make_decoder(seed, "trained_norm", precision="fp32")
+    dec = util.make_decoder(seed, "trained_norm", precision=precision)
     code = torch.from_numpy(g[tag + "_code"]).cuda()
     pts = torch.from_numpy(g[tag + "_pts"]).cuda()
     inp = torch.cat([code.expand(pts.shape[0], -1), pts], 1)
@@ -68,9 +73,45 @@ def test_trained_norm_weights_fp32_vs_golden(seed):
         assert np.abs(dec(inp, use_net=u).cpu().numpy() - g[tag + "_u%d" % u]).max() <= 2e-4
 
 
+@pytest.mark.parametrize("seed", [0, 1])
+def test_trained_norm_weights_split_operand_parity(seed):
+    """The parity mode on realistic weights: 20,000 points x every use_net x the 12-tuple against the
+    fp64 oracle.  SDF within 1e-4 (north star 1e-3), normals / probabilities within 1e-3 (north star 1e-2), and no
+    sign flip outside the +-2e-5 band in which the reference's own fp32 arithmetic is undecided (its error against
+    fp64 on these inputs is 1.5e-5, see the fp32 rows of tools/x2_check.py)."""
+    dec = util.make_decoder(seed, "trained_norm", precision="fp16x2")
+    net = util.oracle_net(seed, "trained_norm", "float64")
+    code = util.trained_code(seed)
+    pts = synth.make_points(20000, seed)
+    total_flips = 0
+    for u in (0, 1, 2, 3):
+        ref = O.forward(net, code.double(), pts.double(), u).numpy()
+        out = dec.query(code.cuda(), pts.cuda(), use_net=u).cpu().numpy().astype(np.float64)
+        err = np.abs(out - ref)
+        flip = (out > 0) != (ref > 0)
+        total_flips += int(flip.sum())
+        print("fp16x2 trained-norm seed %d use_net=%d: max %.3e mean %.3e sign flips %d (|ref| at the flips: %s)"
+              % (seed, u, err.max(), err.mean(), int(flip.sum()), np.abs(ref[flip]).tolist()))
+        assert err.max() <= 1e-4 <= NORTH_STAR_SDF
+        assert not (flip & (np.abs(ref) > 2e-5)).any()
+        occ_ref = O.forward(net, code.double(), pts.double(), u, return_occ=True).numpy()
+        occ = dec.query(code.cuda(), pts.cuda(), use_net=u, return_occ=True).cpu().numpy()
+        scale = max(1.0, float(np.abs(occ_ref).max()))  # use_net 0 / 3 return logits
+        assert np.abs(occ - occ_ref).max() <= 1e-4 * scale
+    assert total_flips <= 2
+    ref12 = O.forward(net, code.double(), pts.double(), None)
+    out12 = dec.query_all(code.cuda(), pts.cuda())
+    for nm, a, b in zip(NAMES, out12, ref12):
+        e = float((a.cpu().double() - b).abs().max())
+        scale = max(1.0, float(b.abs().max()))
+        assert e <= (1e-4 if "sdf" in nm else 1e-3) * scale, (nm, e)
+        assert e <= (NORTH_STAR_SDF if "sdf" in nm else NORTH_STAR_PROB) * scale
+
+
 def test_trained_norm_weights_bf16_error_budget():
-    """bf16 with trained-norm weights: the network amplifies operand rounding (SURVEY §7.3.1:
-    max 5.7e-2, mean 2.8e-3 for single-pass bf16).  Held to that budget, not to 1e-3."""
+    """Single-pass bf16 (the opt-in throughput mode) with trained-norm weights: the network amplifies operand rounding
+    (max 5.7e-2, mean 2.8e-3).  Held to its measured budget, NOT claimed to meet 1e-3: sign flips are
+    counted and bounded."""
     dec = util.make_decoder(0, "trained_norm", precision="bf16")
     net = util.oracle_net(0, "trained_norm", "float64")
     code = util.trained_code(0)
@@ -81,13 +122,14 @@ def test_trained_norm_weights_bf16_error_budget():
     flips = int(((out > 0) != (ref > 0)).sum())
     print("bf16 trained-norm use_net=1: max %.3e mean %.3e p99 %.3e sign flips %d / %d"
           % (err.max(), err.mean(), np.quantile(err, 0.99), flips, len(ref)))
-    assert err.mean() < 1e-2 and err.max() < 0.25
+    assert err.mean() < 1e-2 and err.max() < 0.1
+    assert flips <= 400  # ~0.6 % of the points (measured 128): the iso-surface moves, which is why bf16 is not the default
     out32 = util.make_decoder(0, "trained_norm", precision="fp32").query(code.cuda(), pts.cuda(), use_net=1).cpu().numpy()
     assert np.abs(out32 - ref).max() < 2e-4
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 70001])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2", "bf16"])
+@pytest.mark.parametrize("n", [1, 63, 64, 65, 127, 128, 129, 1000, 70001])
 def test_ragged_sizes(precision, n):
     dec = util.make_decoder(0, "default", precision=precision)
     net = util.oracle_net(0, "default")
@@ -119,7 +161,7 @@ def test_error_contract():
         dec(mixed, use_net=0)
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2", "bf16"])
 @pytest.mark.parametrize("dims", [(12, 12, 12), (6, 9, 11)])
 def test_grid_query_matches_reference_decode_shape(precision, dims):
     from deepjoin_b200.core import reconstruct as R
@@ -127,7 +169,7 @@ def test_grid_query_matches_reference_decode_shape(precision, dims):
     t = "d%dx%dx%d" % dims
     dec = util.make_decoder(0, "trained_norm", precision=precision)
     code = torch.from_numpy(g["code"])
-    tol = 2e-4 if precision == "fp32" else 0.25
+    tol = {"fp32": 2e-4, "fp16x2": 2e-4, "bf16": 0.1}[precision]  # bf16: measured budget on trained-norm weights
     for u in (0, 1, 2, 3):
         v = R.decode_shape(code, dec, dims, use_net=u, batch_size=500, padding=0.1, reshape=False, sigmoid=False)
         ref = g[t + "_u%d_flat" % u]
@@ -155,7 +197,7 @@ def test_grid_points_are_bit_identical_to_numpy_meshgrid(precision):
         assert torch.equal(c, b[lo:hi])
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2", "bf16"])
 def test_decode_samples_host_buffers(precision):
     from deepjoin_b200.core import reconstruct as R
     dec = util.make_decoder(0, "default", precision=precision)
@@ -186,7 +228,16 @@ def test_large_grid_properties_256():
     """BASELINE config 2 size (256^3): size-independent properties instead of the oracle --
     slab queries tile the full query bit-exactly, B = max(C, -T) and R = max(C, T)."""
     from deepjoin_b200.core import reconstruct as R
-    dec = util.make_decoder(0, "trained_norm", precision="bf16")
+    _large_grid_properties("bf16")
+
+
+def test_large_grid_properties_256_split_operand():
+    _large_grid_properties("fp16x2")
+
+
+def _large_grid_properties(precision):
+    from deepjoin_b200.core import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision=precision)
     code = util.trained_code(0)
     dims = (256, 256, 256)
     tot = 256 ** 3
@@ -202,7 +253,7 @@ def test_large_grid_properties_256():
     assert (b.min() < 0) and (b.max() > 0)
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 1e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("fp16x2", 2e-5), ("bf16", 1e-3)])
 def test_latent_size_256_variant(precision, tol):
     """BASELINE configs[4]: CodeLength = 256 (fnet lin0 [512,259], lin3 [253,512]); every use_net branch
     against the oracle restatement."""
@@ -252,12 +303,12 @@ def test_grid_mode_equals_point_mode_for_any_dims_rows_and_branch():
     points return bit-identical values for any (non-cubic) dims, padding, row range, use_net and precision."""
     from hypothesis import given, settings, strategies as st
     from deepjoin_b200.core import reconstruct as R
-    decs = {p: util.make_decoder(1, "trained_norm", precision=p) for p in ("bf16", "fp16", "fp32")}
+    decs = {p: util.make_decoder(1, "trained_norm", precision=p) for p in ("bf16", "fp16", "fp16x2", "fp32")}
     code = util.trained_code(1).cuda()
 
     @settings(max_examples=40, deadline=None, derandomize=True, database=None)
     @given(d0=st.integers(2, 24), d1=st.integers(2, 24), d2=st.integers(2, 24), padding=st.sampled_from([0.0, 0.05, 0.1, 0.3]),
-           u=st.sampled_from([0, 1, 2, 3]), precision=st.sampled_from(["bf16", "fp16", "fp32"]), cut=st.tuples(st.floats(0, 1), st.floats(0, 1)))
+           u=st.sampled_from([0, 1, 2, 3]), precision=st.sampled_from(["bf16", "fp16", "fp16x2", "fp32"]), cut=st.tuples(st.floats(0, 1), st.floats(0, 1)))
     def run(d0, d1, d2, padding, u, precision, cut):
         dec = decs[precision]
         dims = (d0, d1, d2)
