@@ -3,6 +3,7 @@ return types); grid construction, batched decoder queries and marching cubes run
 behind the C ABI.  Line numbers cite the reference file."""
 import ctypes
 import logging
+import threading
 
 import numpy as np
 import torch
@@ -103,14 +104,21 @@ def decode_shape(vec, decoder, dims, use_net=1, batch_size=2 ** 16, padding=0.0,
     return values
 
 
-_mc_work = {}
 _PINNED_MESH_LIMIT = 1 << 28  # larger meshes go to pageable memory
+_tls = threading.local()
 
 
-def _work_for(device_index):
-    w = _mc_work.get(device_index)
+def _work_for(device_index, stream=None):
+    """Marching-cubes / meshing workspace (DjMcWork) of the calling THREAD for this device and stream: a workspace
+    is one call at a time, so nothing is shared between threads or between streams (no process-global state;
+    SURVEY 8b).  ``stream=None``: the host-facing create_mesh path, which runs on the workspace's own stream."""
+    cache = getattr(_tls, "work", None)
+    if cache is None:
+        cache = _tls.work = {}
+    key = (device_index, stream)
+    w = cache.get(key)
     if w is None:
-        w = _mc_work[device_index] = _lib.McWork(device_index)
+        w = cache[key] = _lib.McWork(device_index)
     return w
 
 
@@ -124,10 +132,10 @@ def marching_cubes(volume, level, gradient_direction="descent"):
         raise ValueError("Input volume should be a 3D numpy array.")
     vol = volume.detach().to(torch.float32).contiguous()
     dev = vol.device
-    w = _work_for(dev.index)
     nv, nf = ctypes.c_int64(), ctypes.c_int64()
     with torch.cuda.device(dev):
         st = _lib.stream_ptr()
+        w = _work_for(dev.index, st)
         _lib.check(_lib.lib().dj_mc_count(w.handle, vol.data_ptr(), vol.shape[0], vol.shape[1], vol.shape[2], 0, 0,
                                           float(level), 1, ctypes.byref(nv), ctypes.byref(nf), st))
         verts = torch.empty((nv.value, 3), device=dev, dtype=torch.float32)
@@ -187,11 +195,11 @@ def merge_vertices(vertices, faces):
     v = vertices.detach().to(torch.float64).contiguous().clone()
     f = faces.detach().to(torch.int32).contiguous().clone()
     dev = v.device
-    w = _work_for(dev.index)
     n = ctypes.c_int64()
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().dj_mesh_merge_vertices(w.handle, v.data_ptr(), v.shape[0], f.data_ptr(), f.shape[0],
-                                                     ctypes.byref(n), _lib.stream_ptr()))
+        st = _lib.stream_ptr()
+        _lib.check(_lib.lib().dj_mesh_merge_vertices(_work_for(dev.index, st).handle, v.data_ptr(), v.shape[0], f.data_ptr(),
+                                                     f.shape[0], ctypes.byref(n), st))
     return v[:n.value], f
 
 

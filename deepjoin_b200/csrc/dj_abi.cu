@@ -2,6 +2,10 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
 #include <thread>
 #include <cerrno>
+#include <cmath>
+#include <map>
+#include <memory>
+#include <mutex>
 #include "common.cuh"
 #include "mlp_simt.cuh"
 #include "mlp_tc.cuh"
@@ -18,6 +22,21 @@ using namespace dj;
 constexpr int DJ_MAX_BATCH = 64;  // shapes per launch of the batched latent step
 
 // ====================================================================== pack
+// what one call (one stream) writes: per-shape constants of up to DJ_MAX_BATCH codes, the device error word of the
+// watchdogs, grow-only workspaces
+struct DjCtx {
+  float4* tables = nullptr;
+  unsigned int* err = nullptr;
+  DevBuf ws_fwd, ws_lat, ws_host, ws_mask;
+  PinBuf pin_host;  // staging of dj_decode_samples_host
+  ~DjCtx() {
+    if (tables) cudaFree(tables);
+    if (err) cudaFree(err);
+    ws_fwd.release(); ws_lat.release(); ws_host.release(); ws_mask.release();
+    pin_host.release();
+  }
+};
+
 struct DjPack {
   DjNetDesc desc{};
   int device = 0;
@@ -46,15 +65,39 @@ struct DjPack {
   int lat_n_prog = 0;
   int lat_net1_lo = 0, lat_net1_hi = 0;  // program entries of the second net (forward + backward)
   bool lat_attr_set = false;
-  // per-call shape constants + device error word
-  float4* tables = nullptr;
-  unsigned int* err = nullptr;
   simt::FoldParams fold{};
-  // workspaces (grow only)
-  DevBuf ws_fwd, ws_lat, ws_host, ws_vol, ws_mask;
-  PinBuf pin_host;  // staging of dj_decode_samples_host
   bool tc_attr_set2 = false;
+  // Everything a call writes lives in a per-stream context (re-entrant across streams, no shared mutable
+  // state): calls on one stream are ordered by the stream and share a context; calls on different streams (or host
+  // threads driving different streams) get different ones and may overlap.  The pack itself is read-only after
+  // dj_pack_create.
+  std::mutex mu;
+  std::map<cudaStream_t, std::shared_ptr<DjCtx>> ctxs;
+  // host-buffer entry points (dj_decode_samples_host*): two private streams sharing one context; concurrent host
+  // calls on one pack are serialised by host_mu
+  std::mutex host_mu;
+  cudaStream_t host_streams[2] = {nullptr, nullptr};
+  cudaEvent_t host_events[2] = {nullptr, nullptr};
+  DjCtx* cx(cudaStream_t st);
 };
+
+DjCtx* DjPack::cx(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = ctxs.find(st);
+  if (it != ctxs.end()) return it->second.get();
+  auto c = std::make_shared<DjCtx>();
+  if (cudaMalloc((void**)&c->tables, (size_t)DJ_MAX_BATCH * 3 * 512 * sizeof(float4)) != cudaSuccess) return nullptr;
+  if (cudaMalloc((void**)&c->err, sizeof(unsigned int)) != cudaSuccess || cudaMemset(c->err, 0, sizeof(unsigned int)) != cudaSuccess) {
+    cudaFree(c->tables);
+    c->tables = nullptr;
+    return nullptr;
+  }
+  ctxs[st] = c;
+  return c.get();
+}
+#define DJ_CTX(var, pack, st)                                                         \
+  DjCtx* var = (pack)->cx(st);                                                        \
+  if (!var) return dj::fail(DJ_ERR_CUDA, "%s:%d per-stream context allocation failed", __FILE__, __LINE__)
 
 static void free_pack(DjPack* p) {
   if (!p) return;
@@ -76,15 +119,12 @@ static void free_pack(DjPack* p) {
     if (p->lat_stream[r]) cudaFree(p->lat_stream[r]);
     if (p->lat_stream_h[r]) cudaFree(p->lat_stream_h[r]);
   }
-  if (p->tables) cudaFree(p->tables);
-  if (p->err) cudaFree(p->err);
   if (p->prof) cudaFree(p->prof);
-  p->ws_fwd.release();
-  p->ws_lat.release();
-  p->ws_host.release();
-  p->pin_host.release();
-  p->ws_vol.release();
-  p->ws_mask.release();
+  for (int i = 0; i < 2; i++) {
+    if (p->host_streams[i]) cudaStreamDestroy(p->host_streams[i]);
+    if (p->host_events[i]) cudaEventDestroy(p->host_events[i]);
+  }
+  p->ctxs.clear();
   delete p;
 }
 
@@ -271,9 +311,6 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
   p->fold.src[0] = {p->fW[0], p->fB[0], L + 3, 0, L, L, 0};
   p->fold.src[1] = {p->fW[li], p->fB[li], H, K3, L, K3 + L, 0};
   p->fold.src[2] = {p->hW[0], p->hB[0], Lb + 3, 0, Lb, Lb, L};
-  DJ_TRY(cudaMalloc((void**)&p->tables, (size_t)DJ_MAX_BATCH * 3 * 512 * sizeof(float4)));  // per-shape constants of up to DJ_MAX_BATCH codes
-  DJ_TRY(cudaMalloc((void**)&p->err, sizeof(unsigned int)));
-  DJ_TRY(cudaMemset(p->err, 0, sizeof(unsigned int)));
   DJ_TRY(cudaMalloc((void**)&p->prof, (size_t)prop.multiProcessorCount * 16 * sizeof(unsigned long long)));
   DJ_TRY(cudaMemset(p->prof, 0, (size_t)prop.multiProcessorCount * 16 * sizeof(unsigned long long)));
 
@@ -555,14 +592,16 @@ struct GridSpec {
 
 static int check_err_word(DjPack* p, cudaStream_t st) {
   unsigned int h = 0;
-  DJ_CUDA(cudaMemcpyAsync(&h, p->err, sizeof h, cudaMemcpyDeviceToHost, st));
+  DJ_CTX(c, p, st);
+  DJ_CUDA(cudaMemcpyAsync(&h, c->err, sizeof h, cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaStreamSynchronize(st));
   if (h) return fail(DJ_ERR_DEVICE, "device watchdog fired: 0x%08x", h);
   return DJ_OK;
 }
 
 static int launch_fold(DjPack* p, const float* code_dev, cudaStream_t st) {
-  simt::fold_kernel<<<(3 * 512 * 32 + 255) / 256, 256, 0, st>>>(p->fold, code_dev, p->tables);
+  DJ_CTX(c, p, st);
+  simt::fold_kernel<<<(3 * 512 * 32 + 255) / 256, 256, 0, st>>>(p->fold, code_dev, c->tables);
   DJ_LAUNCHED();
   return DJ_OK;
 }
@@ -581,7 +620,8 @@ static int launch_sgemm(const float* A, int lda, const float* B, int ldb, float*
 static int fp32_forward(DjPack* p, const float* xyz, int64_t n, int net_mask, float* const* fH, float* const* hH,
                         float* yC, float* yT, cudaStream_t st) {
   const float slope = p->desc.slope;
-  const float* tabf = reinterpret_cast<const float*>(p->tables);
+  DJ_CTX(c, p, st);
+  const float* tabf = reinterpret_cast<const float*>(c->tables);
   const int H = p->H, K3 = p->K3, li = p->desc.latent_in;
   int rc;
   if (net_mask & 1) {
@@ -620,6 +660,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
                        const HeadCfg& head, int net_mask, int precision, float* out_dev, cudaStream_t st, bool do_fold = true) {
   if (n <= 0) return DJ_OK;
   int rc;
+  DJ_CTX(cx, p, st);
   if (do_fold && (rc = launch_fold(p, code_dev, st))) return rc;
   if (precision == DJ_PREC_BF16 || precision == DJ_PREC_FP16 || precision == DJ_PREC_FP16X2) {
     const bool f16 = precision == DJ_PREC_FP16;
@@ -635,7 +676,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     P.grid_mode = G.on;
     if (const char* e = getenv("DEEPJOIN_B200_DEBUG")) P.debug = atoi(e);
     P.bias = p->bias_dev;
-    P.tables = p->tables;
+    P.tables = cx->tables;
     P.xyz = xyz_dev;
     P.n = n;
     P.d0 = G.d0; P.d1 = G.d1; P.d2 = G.d2;
@@ -643,7 +684,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     P.stop = G.stop; P.offs = G.offs; P.r_lo = G.r_lo;
     P.head = head;
     P.out = out_dev;
-    P.err = p->err;
+    P.err = cx->err;
     P.prof = p->prof;
     const int tile_pts = x2 ? tc2::TILE_PTS_X2 : tc2::TILE_M;
     const int64_t ntiles = (n + tile_pts - 1) / tile_pts;
@@ -668,8 +709,8 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
   const int64_t c = std::min(CH, n);
   const size_t act = (size_t)c * 512 * sizeof(float);
   const size_t need = 2 * act + 2 * (size_t)c * 8 * sizeof(float) + (size_t)c * 3 * sizeof(float);
-  DJ_CUDA(p->ws_fwd.reserve(need));
-  uint8_t* w = p->ws_fwd.as<uint8_t>();
+  DJ_CUDA(cx->ws_fwd.reserve(need));
+  uint8_t* w = cx->ws_fwd.as<uint8_t>();
   float* bufA = reinterpret_cast<float*>(w);
   float* bufB = reinterpret_cast<float*>(w + act);
   float* yC = reinterpret_cast<float*>(w + 2 * act);
@@ -770,26 +811,30 @@ extern "C" int dj_decode_samples_host_strided(DjPack* p, const float* code_host,
   // device: [code | 2 x (pts f64 | pts f32 | out f32 | out f64)]
   const size_t o_p64 = 0, o_p32 = o_p64 + (size_t)c * 24, o_o32 = o_p32 + (size_t)c * 12,
                o_o64 = (o_o32 + (size_t)c * 4 + 15) & ~(size_t)15, half = (o_o64 + (size_t)c * 8 + 255) & ~(size_t)255;
-  DJ_CUDA(p->ws_host.reserve(1024 + 2 * half));
-  uint8_t* w0 = p->ws_host.as<uint8_t>();
+  // one host-buffer call at a time per pack (private streams, staging buffers); device-pointer calls on other
+  // streams are not affected: they work in their own contexts
+  std::lock_guard<std::mutex> host_lock(p->host_mu);
+  for (int i = 0; i < 2; i++) {
+    if (!p->host_streams[i]) DJ_CUDA(cudaStreamCreateWithFlags(&p->host_streams[i], cudaStreamNonBlocking));
+    if (!p->host_events[i]) DJ_CUDA(cudaEventCreateWithFlags(&p->host_events[i], cudaEventDisableTiming));
+  }
+  cudaStream_t sts[2] = {p->host_streams[0], p->host_streams[1]};
+  cudaEvent_t done[2] = {p->host_events[0], p->host_events[1]};
+  DJ_CTX(hc, p, sts[0]);
+  {  // both private streams work on the same per-shape tables (folded once, below) and staging buffers
+    std::lock_guard<std::mutex> lock(p->mu);
+    p->ctxs[sts[1]] = p->ctxs[sts[0]];
+  }
+  DJ_CUDA(hc->ws_host.reserve(1024 + 2 * half));
+  uint8_t* w0 = hc->ws_host.as<uint8_t>();
   const bool stage_in = n > 0 && !is_pinned_host(pts_host), stage_out = n > 0 && !is_pinned_host(out_host);
   // pinned: [code 1 KB | 2 x (pts f64 | out f64)]
   const size_t ph = (size_t)c * 32;
-  DJ_CUDA(p->pin_host.reserve(1024 + 2 * ph));
-  uint8_t* h0 = p->pin_host.as<uint8_t>();
+  DJ_CUDA(hc->pin_host.reserve(1024 + 2 * ph));
+  uint8_t* h0 = hc->pin_host.as<uint8_t>();
   memcpy(h0, code_host, nc * sizeof(float));
-  cudaStream_t sts[2] = {nullptr, nullptr};
-  cudaEvent_t done[2] = {nullptr, nullptr};
-  for (int i = 0; i < 2; i++) {
-    DJ_CUDA(cudaStreamCreateWithFlags(&sts[i], cudaStreamNonBlocking));
-    DJ_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
-  }
   auto cleanup = [&](int rc) {
-    for (int i = 0; i < 2; i++) {
-      cudaStreamSynchronize(sts[i]);
-      cudaStreamDestroy(sts[i]);
-      cudaEventDestroy(done[i]);
-    }
+    for (int i = 0; i < 2; i++) cudaStreamSynchronize(sts[i]);
     return rc;
   };
   if (cudaMemcpyAsync(w0, h0, nc * sizeof(float), cudaMemcpyHostToDevice, sts[0]) != cudaSuccess)
@@ -849,7 +894,7 @@ extern "C" int dj_decode_samples_host_strided(DjPack* p, const float* code_host,
   }
   int rc = cleanup(DJ_OK);
   if (rc) return rc;
-  if (precision != DJ_PREC_FP32) return check_err_word(p, 0);
+  if (precision != DJ_PREC_FP32) return check_err_word(p, sts[0]);
   return DJ_OK;
 }
 
@@ -865,12 +910,13 @@ struct LatWs {
 };
 
 // small: the tensor-core path keeps no activations in global memory
-static int carve_latent(DjPack* p, int64_t n, LatWs& W, bool small = false) {
+static int carve_latent(DjPack* p, int64_t n, LatWs& W, cudaStream_t st, bool small = false) {
+  DJ_CTX(c, p, st);
   const int nf = p->desc.f_layers - 1, nh = p->desc.h_layers - 1;
   const size_t act = small ? 0 : (size_t)n * 512;
   const size_t floats = (size_t)(nf + nh + 2) * act + 4 * (size_t)n * 8 + 3 * 512 + 8 + 256 + 8 + (size_t)n * 7 + 64;
-  DJ_CUDA(p->ws_lat.reserve(floats * sizeof(float)));
-  float* q = p->ws_lat.as<float>();
+  DJ_CUDA(c->ws_lat.reserve(floats * sizeof(float)));
+  float* q = c->ws_lat.as<float>();
   W.fH.resize(nf + 1); W.hH.resize(nh + 1);
   for (int l = 0; l < nf; l++) { W.fH[l] = q; q += act; }
   for (int l = 0; l < nh; l++) { W.hH[l] = q; q += act; }
@@ -948,10 +994,11 @@ struct LatTcWs {
   float *acc, *grad, *terms;
   const float** ptrs;  // xyz[S] | sdf[S] | nrm[S]
 };
-static int carve_latent_tc(DjPack* p, int S, LatTcWs& W) {
+static int carve_latent_tc(DjPack* p, int S, LatTcWs& W, cudaStream_t st) {
+  DJ_CTX(c, p, st);
   const size_t floats = (size_t)S * (lat2::ACC_STRIDE + 256 + 8) + 64;
-  DJ_CUDA(p->ws_lat.reserve(floats * sizeof(float) + (size_t)3 * S * sizeof(void*) + 256));
-  float* q = p->ws_lat.as<float>();
+  DJ_CUDA(c->ws_lat.reserve(floats * sizeof(float) + (size_t)3 * S * sizeof(void*) + 256));
+  float* q = c->ws_lat.as<float>();
   W.acc = q; q += (size_t)S * lat2::ACC_STRIDE;
   W.grad = q; q += (size_t)S * 256;
   W.terms = q; q += (size_t)S * 8;
@@ -973,14 +1020,15 @@ static int upload_ptrs(LatTcWs& W, int S, const float* const* xyz, const float* 
 static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int32_t* idx, int64_t idx_stride, int64_t n,
                              const DjLatentCfg* cfg, LatTcWs& W, cudaStream_t st) {
   const int C = p->L + p->Lb;
-  simt::fold_kernel<<<dim3((3 * 512 * 32 + 255) / 256, S), 256, 0, st>>>(p->fold, codes_dev, p->tables, C);
+  DJ_CTX(c, p, st);
+  simt::fold_kernel<<<dim3((3 * 512 * 32 + 255) / 256, S), 256, 0, st>>>(p->fold, codes_dev, c->tables, C);
   DJ_LAUNCHED();
   DJ_CUDA(cudaMemsetAsync(W.acc, 0, (size_t)S * lat2::ACC_STRIDE * sizeof(float), st));
   const int64_t tps = (n + lat2::TILE_M - 1) / lat2::TILE_M;
   const int64_t ntiles = tps * S;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);
   const int64_t passes = (ntiles + grid - 1) / grid;
-  DJ_CUDA(p->ws_mask.reserve((size_t)passes * grid * lat2::MASK_LAYERS * 8 * 128 * sizeof(unsigned long long)));
+  DJ_CUDA(c->ws_mask.reserve((size_t)passes * grid * lat2::MASK_LAYERS * 8 * 128 * sizeof(unsigned long long)));
   lat2::Params P;
   memset(&P, 0, sizeof P);
   memcpy(P.prog, p->lat_prog, sizeof(lat2::Layer) * p->lat_n_prog);
@@ -990,16 +1038,16 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
   P.stream[0] = half_fwd ? p->lat_stream_h[0] : p->lat_stream[0];
   P.stream[1] = half_fwd ? p->lat_stream_h[1] : p->lat_stream[1];
   P.bias = p->bias_dev;
-  P.tables = p->tables;
+  P.tables = c->tables;
   P.xyz = W.ptrs; P.sdf = W.ptrs + S; P.nrm = W.ptrs + 2 * S;
   P.idx = idx; P.idx_stride = idx_stride;
   P.n = n;
   P.n_shapes = S; P.tiles_per_shape = (int32_t)tps;
   P.loss = simt::LossCfg{cfg->lambda1, cfg->lambda3, cfg->clamp_dist, p->desc.slope, 1.0f / (float)n, cfg->loss_kind};
   if (cfg->loss_kind == DJ_LOSS_DEEPSDF) { P.skip_lo = p->lat_net1_lo; P.skip_hi = p->lat_net1_hi; }
-  P.masks = p->ws_mask.as<unsigned long long>();
+  P.masks = c->ws_mask.as<unsigned long long>();
   P.acc = W.acc;
-  P.err = p->err;
+  P.err = c->err;
   if (!p->lat_attr_set) {
     DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
     DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
@@ -1039,7 +1087,7 @@ extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz
   cudaStream_t st = (cudaStream_t)stream;
   if (cfg->precision != DJ_PREC_FP32) {  // tensor cores (bf16 operands; gradients underflow in IEEE half)
     LatTcWs T;
-    if ((rc = carve_latent_tc(p, 1, T))) return rc;
+    if ((rc = carve_latent_tc(p, 1, T, st))) return rc;
     if ((rc = upload_ptrs(T, 1, &xyz_dev, &sdf_dev, &nrm_dev, st))) return rc;
     if ((rc = latent_fwd_bwd_tc(p, 1, code_dev, nullptr, 0, n, cfg, T, st))) return rc;
     if ((rc = check_err_word(p, st))) return rc;
@@ -1048,7 +1096,7 @@ extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz
     return DJ_OK;
   }
   LatWs W;
-  if ((rc = carve_latent(p, n, W))) return rc;
+  if ((rc = carve_latent(p, n, W, st))) return rc;
   if ((rc = latent_fwd_bwd(p, code_dev, xyz_dev, sdf_dev, nrm_dev, n, cfg, W, st))) return rc;
   DJ_CUDA(cudaMemcpyAsync(grad_dev, W.grad, (p->L + p->Lb) * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (loss_terms_dev) DJ_CUDA(cudaMemcpyAsync(loss_terms_dev, W.terms, 5 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1077,7 +1125,7 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
   if (cfg->precision != DJ_PREC_FP32) {
     // all shapes in one launch per iteration; the kernel gathers every shape's mini-batch rows itself
     LatTcWs T;
-    if ((rc = carve_latent_tc(p, n_shapes, T))) return rc;
+    if ((rc = carve_latent_tc(p, n_shapes, T, st))) return rc;
     if ((rc = upload_ptrs(T, n_shapes, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, st))) return rc;
     const int64_t idx_stride = (int64_t)cfg->num_iterations * n;
     for (int e = 0; e < cfg->num_iterations; e++) {
@@ -1087,11 +1135,13 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
                                                   (long long)log_rows * 8);
       DJ_LAUNCHED();
     }
-    return DJ_OK;
+    // a device watchdog that fired during the loop must not go unnoticed (this synchronises the stream once per
+    // optimisation; the caller reads the codes right after anyway)
+    return check_err_word(p, st);
   }
   // fp32 (reference arithmetic): shape after shape
   LatWs W;
-  if ((rc = carve_latent(p, n, W))) return rc;
+  if ((rc = carve_latent(p, n, W, st))) return rc;
   for (int s = 0; s < n_shapes; s++) {
     float* code = codes_dev + (size_t)s * C;
     const int32_t* idx = idx_dev + (size_t)s * cfg->num_iterations * n;
@@ -1247,7 +1297,11 @@ extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int
 struct DjMcWork {
   int device = 0;
   mc::Dims D{};
-  DevBuf var, counts, offs, edge, misc, verts, faces, merge, wide;
+  DevBuf var, counts, offs, edge, misc, verts, faces, merge, wide, volbuf;
+  // host-facing create_mesh entry points (dj_create_mesh_count / fetch): this workspace's own stream, so that two
+  // host threads meshing with one DjPack (each with its own DjMcWork) neither share per-shape tables nor order
+  // against each other
+  cudaStream_t own_stream = nullptr;
   double* v64 = nullptr;  // create_mesh: final float64 vertices on the device (inside verts / merge)
   int64_t nblocks = 0, nv = 0, nf = 0;
   int bpp = 0;  // blocks per cell layer (grid.x of the marching-cubes kernels; grid.y = cell layers)
@@ -1264,13 +1318,21 @@ extern "C" int dj_mc_create(int device, DjMcWork** out) {
   if (device < 0 || device >= ndev) return fail(DJ_ERR_INVALID, "device %d out of range", device);
   DjMcWork* w = new DjMcWork();
   w->device = device;
+  {
+    DeviceGuard g(device);
+    if (cudaStreamCreateWithFlags(&w->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete w;
+      return fail(DJ_ERR_CUDA, "dj_mc_create: cannot create a stream on device %d", device);
+    }
+  }
   *out = w;
   return DJ_OK;
 }
 extern "C" int dj_mc_destroy(DjMcWork* w) {
   if (!w) return DJ_OK;
   DeviceGuard g(w->device);
-  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge, &w->wide}) b->release();
+  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge, &w->wide, &w->volbuf}) b->release();
+  if (w->own_stream) cudaStreamDestroy(w->own_stream);
   delete w;
   return DJ_OK;
 }
@@ -1445,11 +1507,11 @@ extern "C" int dj_create_mesh_count(DjPack* p, DjMcWork* w, const float* code_ho
   if (!p || !w || !code_host || !n_verts || !n_faces) return fail(DJ_ERR_INVALID, "dj_create_mesh_count: null argument");
   if (p->device != w->device) return fail(DJ_ERR_INVALID, "pack and marching-cubes workspace live on different devices");
   DeviceGuard g(p->device);
-  cudaStream_t st = 0;
+  cudaStream_t st = w->own_stream;
   const int64_t tot = (int64_t)d0 * d1 * d2;
   const int nc = p->L + p->Lb;
-  DJ_CUDA(p->ws_vol.reserve((size_t)tot * sizeof(float) + 1024));
-  float* code_dev = p->ws_vol.as<float>();
+  DJ_CUDA(w->volbuf.reserve((size_t)tot * sizeof(float) + 1024));
+  float* code_dev = w->volbuf.as<float>();
   float* vol = code_dev + 256;
   DJ_CUDA(cudaMemcpyAsync(code_dev, code_host, nc * sizeof(float), cudaMemcpyHostToDevice, st));
   const double stop = 1.0 + (padding * 2), offs = 0.5 + padding;
@@ -1488,7 +1550,7 @@ extern "C" int dj_create_mesh_count(DjPack* p, DjMcWork* w, const float* code_ho
 extern "C" int dj_create_mesh_fetch(DjMcWork* w, double* verts_host, int32_t* faces_host) {
   if (!w || !w->counted || !w->v64 || !verts_host || !faces_host) return fail(DJ_ERR_INVALID, "dj_create_mesh_fetch: bad argument");
   DeviceGuard g(w->device);
-  cudaStream_t st = 0;
+  cudaStream_t st = w->own_stream;
   DJ_CUDA(cudaMemcpyAsync(verts_host, w->v64, (size_t)w->nv * 3 * sizeof(double), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaMemcpyAsync(faces_host, w->faces.as<int>(), (size_t)w->nf * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   DJ_CUDA(cudaStreamSynchronize(st));
@@ -1510,7 +1572,7 @@ extern "C" int dj_create_mesh_fetch64(DjMcWork* w, double* verts_host, int64_t* 
   if (!w || !w->counted || !w->v64 || !verts_host || !faces_host || !nonfinite)
     return fail(DJ_ERR_INVALID, "dj_create_mesh_fetch64: bad argument");
   DeviceGuard g(w->device);
-  cudaStream_t st = 0;
+  cudaStream_t st = w->own_stream;
   const int64_t nf3 = w->nf * 3, nv3 = w->nv * 3;
   DJ_CUDA(w->wide.reserve((size_t)nf3 * sizeof(int64_t) + 16));
   int64_t* f64 = w->wide.as<int64_t>();

@@ -56,7 +56,7 @@ __global__ void grid_points_kernel(float* __restrict__ xyz, int64_t n, int64_t r
   const int j = (int)(q % d0);
   const int i = (int)(q / d0);
   auto lin = [&](int t, int d, double step) {
-    double v = (t == d - 1) ? stop : __dmul_rn((double)t, step);
+    double v = (d > 1 && t == d - 1) ? stop : __dmul_rn((double)t, step);  // np.linspace(0, stop, 1) is [0.0]
     return (float)__dsub_rn(v, offs);
   };
   xyz[3 * g + 0] = lin(j, d0, step0);

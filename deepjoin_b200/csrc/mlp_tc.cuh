@@ -51,7 +51,7 @@ struct TcNet {
 };
 __device__ __forceinline__ float lin_axis(int t, int d, double step, double stop, double offs) {
   // np.linspace(0, stop, d)[t] - offs in float64, no fused multiply-add, then f32
-  double v = (t == d - 1) ? stop : __dmul_rn((double)t, step);
+  double v = (d > 1 && t == d - 1) ? stop : __dmul_rn((double)t, step);  // np.linspace(0, stop, 1) is [0.0]
   return (float)__dsub_rn(v, offs);
 }
 

@@ -180,7 +180,24 @@ def test_grid_query_matches_reference_decode_shape(precision, dims):
     assert np.abs(v - g[t + "_u1_reshape_sig"]).max() <= tol
 
 
-@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+@pytest.mark.parametrize("dims", [(1, 9, 7), (8, 1, 5), (4, 6, 1), (1, 1, 1)])
+def test_grid_query_with_an_axis_of_length_one(precision, dims):
+    """np.linspace(0, stop, 1) is [0.0] (not [stop]): a 2-D slice query must evaluate the plane the reference does
+    (fixture made by the reference itself, tests/golden/make_golden_grid_extra.py)."""
+    from deepjoin_b200.core import reconstruct as R
+    g = np.load(os.path.join(G, "grid_extra.npz"))
+    t = "d%dx%dx%d" % dims
+    dec = util.make_decoder(0, "trained_norm", precision=precision)
+    code = torch.from_numpy(g["code"])
+    assert np.array_equal(R.get_query_points(dims, 0.1), g[t + "_pts"])
+    for u in (1, 3):
+        v = R.decode_shape(code, dec, dims, use_net=u, batch_size=500, padding=0.1, reshape=False, sigmoid=False)
+        assert v.shape == g[t + "_u%d_flat" % u].shape
+        assert np.abs(v - g[t + "_u%d_flat" % u]).max() <= 2e-4
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16", "fp16x2"])
 def test_grid_points_are_bit_identical_to_numpy_meshgrid(precision):
     """In-kernel coordinates == np.meshgrid/linspace coordinates: the same kernel fed the numpy
     points must return bit-identical values."""

@@ -47,6 +47,18 @@ def test_bad_use_net_raises():
         O.forward(net, synth.make_code(0), synth.make_points(4), use_net=4)
 
 
+@pytest.mark.parametrize("dims", [(1, 9, 7), (8, 1, 5), (4, 6, 1), (1, 1, 1)])
+def test_grid_layout_with_an_axis_of_length_one(dims):
+    g = np.load(os.path.join(G, "grid_extra.npz"))
+    t = "d%dx%dx%d" % dims
+    assert np.array_equal(O.get_query_points(dims, 0.1), g[t + "_pts"])
+    net = O.fold(synth.make_state_dict(0, "trained_norm"))
+    code = torch.from_numpy(g["code"])
+    for u in (1, 3):
+        v = O.decode_shape(net, code, dims, use_net=u, batch_size=500, padding=0.1, reshape=False, sigmoid=False)
+        assert np.abs(v - g[t + "_u%d_flat" % u]).max() < 5e-5
+
+
 @pytest.mark.parametrize("dims", [(12, 12, 12), (6, 9, 11)])
 def test_grid_layout(dims):
     g = np.load(os.path.join(G, "grid.npz"))
