@@ -72,9 +72,13 @@ __device__ __forceinline__ int cube_variant(const double (&f)[8]) {
   const int na = DJ_MC_NAMB[cfg];
   for (int a = 0; a < na; a++) {
     const unsigned char* c = DJ_MC_FACE[DJ_MC_AMBFACE[cfg][a]];
+    // Lewiner's test_face: with A, C one diagonal and B, D the other, the corners above the level are joined through
+    // the face when |AC - BD| < FLT_EPSILON (his dead band) or the face-centre saddle (AC - BD) / (A + C - B - D)
+    // is positive; products and difference rounded separately (no fused multiply-add), as the C library computes them
     const double p02 = __dmul_rn(f[c[0]], f[c[2]]);
     const double p13 = __dmul_rn(f[c[1]], f[c[3]]);
-    const bool joined = ((cfg >> c[0]) & 1) ? (p02 > p13) : (p13 > p02);
+    const double det = __dsub_rn(p02, p13);
+    const bool joined = (fabs(det) < FLT_EPS_D) || (((cfg >> c[0]) & 1) ? (det > 0.0) : (det < 0.0));
     var += joined ? (1 << a) : 0;
   }
   return var;

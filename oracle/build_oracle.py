@@ -10,7 +10,7 @@ LIB = os.path.join(OUT, "libmc_oracle.so")
 
 def build(force=False):
     os.makedirs(OUT, exist_ok=True)
-    srcs = [os.path.join(HERE, "mc_oracle.c"), os.path.join(HERE, "..", "deepjoin_b200", "csrc", "mc_tables.h")]
+    srcs = [os.path.join(HERE, "mc_oracle.c")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(LIB) >= os.path.getmtime(s) for s in srcs):
         return LIB
     subprocess.check_call(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", LIB, srcs[0], "-lm"])

@@ -11,7 +11,11 @@
  *   - vertex position = inverse-distance weights 1/(FLT_EPSILON+|v-level|) in
  *     double, stored as float32, columns (axis0, axis1, axis2) in index units,
  *   - 'descent' reverses each face, level outside [min,max] / no surface errors.
- * The case tables come from tools/gen_mc_tables.py (per-face asymptotic decider).
+ *   - ambiguous faces: Lewiner's test_face -- corners above the level joined across a face iff
+ *     |AC - BD| < FLT_EPSILON or the face-centre saddle value is positive.
+ * The case tables are NOT the product's: they are derived by oracle/mc_case_tables.py (its own statement of the
+ * Lorensen-Cline table and of the joined variants) and handed to this sweep at run time (dj_oracle_mc_set_tables).
+ * Not restated: Lewiner's interior tests (tunnel sub-cases) and his tilings of the joined sub-cases.
  *
  * Build: gcc -O2 -ffp-contract=off -shared -fPIC (oracle/build_oracle.py).
  */
@@ -20,7 +24,33 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
-#include "../deepjoin_b200/csrc/mc_tables.h"
+
+/* Lewiner numbering, written out here (nothing is shared with the product's sources) */
+static const unsigned char DJ_MC_CORNER[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}, {0, 1, 1}};
+static const unsigned char DJ_MC_EDGE[12][2] = {{0, 1}, {1, 2}, {2, 3}, {3, 0}, {4, 5}, {5, 6}, {6, 7}, {7, 4}, {0, 4}, {1, 5}, {2, 6}, {3, 7}};
+/* case tables, set by dj_oracle_mc_set_tables (copied) */
+static int *T_VARBASE, *T_NAMB, *T_AMBFACE, *T_NTRI, *T_TRI, *T_FACE;
+#define DJ_MC_VARBASE T_VARBASE
+#define DJ_MC_NAMB T_NAMB
+#define DJ_MC_AMBFACE(cfg, a) T_AMBFACE[(cfg) * 6 + (a)]
+#define DJ_MC_NTRI T_NTRI
+#define DJ_MC_TRI(var, i) T_TRI[(var) * 36 + (i)]
+
+static int *dup_ints(const int *src, int n) {
+  int *d = (int *)malloc(sizeof(int) * (size_t)n);
+  memcpy(d, src, sizeof(int) * (size_t)n);
+  return d;
+}
+void dj_oracle_mc_set_tables(const int *var_base, const int *n_amb, const int *amb_face, const int *n_tri,
+                             const int *tri, int n_variants, const int *face_corners) {
+  free(T_VARBASE); free(T_NAMB); free(T_AMBFACE); free(T_NTRI); free(T_TRI); free(T_FACE);
+  T_VARBASE = dup_ints(var_base, 256);
+  T_NAMB = dup_ints(n_amb, 256);
+  T_AMBFACE = dup_ints(amb_face, 256 * 6);
+  T_NTRI = dup_ints(n_tri, n_variants);
+  T_TRI = dup_ints(tri, n_variants * 36);
+  T_FACE = dup_ints(face_corners, 24);
+}
 
 typedef struct { float *v; int32_t *f; int64_t nv, nf, capv, capf; } Mesh;
 
@@ -36,11 +66,13 @@ static void push_f(Mesh *m, int32_t a, int32_t b, int32_t c) {
 /* joined (positive diagonal connected through the face centre)? products of the
  * two diagonals, each rounded once; no fused multiply-add. */
 static int face_joined(const double *f, int face, int cfg) {
-  const unsigned char *c = DJ_MC_FACE[face];
+  const int *c = T_FACE + 4 * face;
   double p02 = f[c[0]] * f[c[2]];
   double p13 = f[c[1]] * f[c[3]];
-  if ((cfg >> c[0]) & 1) return p02 > p13; /* corners 0,2 are the positive diagonal */
-  return p13 > p02;
+  double det = p02 - p13;
+  if (fabs(det) < (double)FLT_EPSILON) return 1; /* Lewiner's dead band: test_face(+f) true, test_face(-f) false */
+  if ((cfg >> c[0]) & 1) return det > 0; /* corners 0,2 are the diagonal above the level */
+  return det < 0;
 }
 
 /* position of the vertex on edge e relative to the cell origin, (x,y,z) order:
@@ -61,7 +93,7 @@ int dj_oracle_mc_variant(const double *f) {
   for (int i = 0; i < 8; i++) if (f[i] > 0) cfg |= 1 << i;
   int var = DJ_MC_VARBASE[cfg], bits = 0;
   for (int a = 0; a < DJ_MC_NAMB[cfg]; a++)
-    if (face_joined(f, DJ_MC_AMBFACE[cfg][a], cfg)) bits |= 1 << a;
+    if (face_joined(f, DJ_MC_AMBFACE(cfg, a), cfg)) bits |= 1 << a;
   return var + bits;
 }
 
@@ -69,7 +101,7 @@ int dj_oracle_mc_variant(const double *f) {
 int dj_oracle_mc(const float *vol, int n0, int n1, int n2, double level, int descent,
                  float **verts, int32_t **faces, int64_t *nV, int64_t *nF) {
   *verts = 0; *faces = 0; *nV = 0; *nF = 0;
-  if (n0 < 2 || n1 < 2 || n2 < 2) return 1;
+  if (n0 < 2 || n1 < 2 || n2 < 2 || !T_TRI) return 1;
   {
     float mn = vol[0], mx = vol[0];
     for (int64_t i = 0; i < (int64_t)n0 * n1 * n2; i++) { if (vol[i] < mn) mn = vol[i]; if (vol[i] > mx) mx = vol[i]; }
@@ -98,7 +130,7 @@ int dj_oracle_mc(const float *vol, int n0, int n1, int n2, double level, int des
       for (int t = 0; t < nt; t++) {
         int32_t id[3];
         for (int k = 0; k < 3; k++) {
-          int e = DJ_MC_TRI[var][t * 3 + k];
+          int e = DJ_MC_TRI(var, t * 3 + k);
           int base[3] = {x, y, z};
           if (e == 12) { /* cell-centre vertex: mean of the cell's edge vertices (edge id order) */
             if (centre_id < 0) {

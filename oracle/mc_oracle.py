@@ -1,10 +1,11 @@
 """ctypes front end of oracle/mc_oracle.c + the create_mesh() post-processing
-(core/reconstruct.py:168-187).  TEST INFRASTRUCTURE ONLY; parity vs scikit-image UNPINNED."""
+(core/reconstruct.py:168-187).  TEST INFRASTRUCTURE ONLY; parity vs scikit-image UNPINNED.
+The sweep's case tables come from oracle/mc_case_tables.py (derived there, not the product's header)."""
 import ctypes
 
 import numpy as np
 
-from . import build_oracle
+from . import build_oracle, mc_case_tables
 
 _lib = None
 
@@ -20,6 +21,11 @@ def lib():
         _lib.dj_oracle_free.argtypes = [ctypes.c_void_p]
         _lib.dj_oracle_mc_variant.argtypes = [ctypes.c_void_p]
         _lib.dj_oracle_mc_variant.restype = ctypes.c_int
+        t = mc_case_tables.build()
+        arr = lambda x: (ctypes.c_int * len(x))(*x)
+        _lib.dj_oracle_mc_set_tables.argtypes = [ctypes.c_void_p] * 5 + [ctypes.c_int, ctypes.c_void_p]
+        _lib.dj_oracle_mc_set_tables(arr(t["var_base"]), arr(t["n_amb"]), arr(t["amb_face"]), arr(t["n_tri"]), arr(t["tri"]),
+                                     len(t["n_tri"]), arr(t["face_corners"]))
     return _lib
 
 
