@@ -23,7 +23,10 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(SRC, "dj_abi.cu")]
+    # dj_abi.cu: kernels + the C ABI; host_sampler.cpp: host-only C++ (numpy's MT19937 stream), compiled by the host
+    # compiler nvcc drives
+    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(SRC, "dj_abi.cu"),
+                                                                     os.path.join(SRC, "host_sampler.cpp")]
     subprocess.check_call(cmd)
     return LIB
 

@@ -3,6 +3,8 @@
 #include <thread>
 #include <cerrno>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -1214,80 +1216,7 @@ extern "C" int dj_host_write_obj(const char* path, const double* verts, int64_t 
   return DJ_OK;
 }
 
-// ---- host: numpy's legacy RandomState.permutation(n), continuing a given MT19937 state -------------------------
-// The reference's per-iteration sampler draws np.random.choice(.., replace=False) and np.random.permutation on
-// 250,000 / 312,500 elements (core/data.py:141-176); numpy's shuffle spends ~20 ns per element in a generic
-// byte-wise swap.  This is the same algorithm on int64 directly (mtrand.pyx _shuffle_raw: for i = n-1 .. 1:
-// j = random_interval(i); swap(x[i], x[j]); random_interval: 32-bit draws masked to the smallest 2^k - 1 >= i,
-// rejected while > i), on the same Mersenne-Twister stream, so a seeded run draws exactly the reference's batches.
-namespace mt {
-struct State {
-  uint32_t* key;
-  int pos;
-};
-static inline void refill(State& s) {
-  uint32_t* k = s.key;
-  const uint32_t UP = 0x80000000u, LO = 0x7fffffffu, MAT = 0x9908b0dfu;
-  int i;
-  uint32_t y;
-  for (i = 0; i < 624 - 397; i++) {
-    y = (k[i] & UP) | (k[i + 1] & LO);
-    k[i] = k[i + 397] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
-  }
-  for (; i < 623; i++) {
-    y = (k[i] & UP) | (k[i + 1] & LO);
-    k[i] = k[i + (397 - 624)] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
-  }
-  y = (k[623] & UP) | (k[0] & LO);
-  k[623] = k[396] ^ (y >> 1) ^ ((y & 1u) ? MAT : 0u);
-  s.pos = 0;
-}
-static inline uint32_t next32(State& s) {
-  if (s.pos == 624) refill(s);
-  uint32_t y = s.key[s.pos++];
-  y ^= (y >> 11);
-  y ^= (y << 7) & 0x9d2c5680u;
-  y ^= (y << 15) & 0xefc60000u;
-  y ^= (y >> 18);
-  return y;
-}
-}  // namespace mt
-
-extern "C" int dj_host_mt19937_permutation(uint32_t* key624, int32_t* pos, int64_t n, int64_t* out) {
-  if (!key624 || !pos || !out || n < 0 || *pos < 0 || *pos > 624) return fail(DJ_ERR_INVALID, "dj_host_mt19937_permutation: bad argument");
-  if (n > 0x7fffffffll) return fail(DJ_ERR_UNSUPPORTED, "dj_host_mt19937_permutation: n > 2^31 - 1");
-  mt::State s{key624, *pos};
-  // int32 work array (half the cache footprint of the int64 result); the swap partners of a block of iterations are
-  // drawn first -- they depend only on the generator -- and prefetched, then the swaps run in order
-  std::vector<int32_t> w((size_t)n);
-  for (int64_t i = 0; i < n; i++) w[i] = (int32_t)i;
-  constexpr int B = 32;
-  uint32_t js[B];
-  int64_t i = n - 1;
-  while (i >= 1) {
-    const int nb = (int)std::min<int64_t>(B, i);
-    for (int b = 0; b < nb; b++) {
-      const uint32_t ii = (uint32_t)(i - b);
-      uint32_t mask = ii;
-      mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
-      uint32_t j;
-      while ((j = (mt::next32(s) & mask)) > ii) {}
-      js[b] = j;
-      __builtin_prefetch(&w[j], 1);
-    }
-    for (int b = 0; b < nb; b++) {
-      const int64_t ii = i - b;
-      const int32_t t = w[js[b]];
-      w[js[b]] = w[ii];
-      w[ii] = t;
-    }
-    i -= nb;
-  }
-  for (int64_t k = 0; k < n; k++) out[k] = w[k];
-  *pos = s.pos;
-  return DJ_OK;
-}
-
+// (the host-side sampler on numpy's MT19937 stream lives in host_sampler.cpp)
 extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int num_iterations, int num_samples,
                                   float uniform_ratio, uint64_t seed, int32_t* idx_dev, void* stream) {
   return sampler::sample_schedule(pool_sdf_dev, pool_n, num_iterations, num_samples, uniform_ratio, seed, idx_dev, (cudaStream_t)stream);

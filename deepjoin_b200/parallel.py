@@ -59,40 +59,110 @@ def _dist():
     return dist if (dist.is_available() and dist.is_initialized()) else None
 
 
-def gather_fragments(verts, faces, top, group=None, dst=0):
+def _exchange_counts(verts, faces, top, group):
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    counts = torch.tensor([verts.shape[0], faces.shape[0], top.shape[0]], dtype=torch.int64, device=verts.device)
+    all_counts = [torch.zeros_like(counts) for _ in range(world)]
+    dist.all_gather(all_counts, counts, group=group)
+    return torch.stack(all_counts).cpu().tolist()
+
+
+def gather_fragments(verts, faces, top, group=None, dst=0, merged=False):
     """Collective.  verts [V,3] float32, faces [F,3] int32 (slab-local ids, seam references
     -2-slot), top [T] int32 (ids of the slab's last-plane edges) -- torch tensors on this rank's
     device.  Returns the list of (verts, faces, top) over ranks on rank `dst`, None elsewhere.
-    Two collectives: an all-gather of the three counts, then ONE gather of a padded int32 buffer
-    (payload is a few MB: latency-bound, so a single call beats three)."""
+
+    The exchange: an all-gather of the three counts, then ONE group of exact-size point-to-point
+    transfers (torch.distributed.batch_isend_irecv = ncclGroupStart / ncclSend / ncclRecv / ncclGroupEnd on GPUs):
+    every fragment is sent once, unpadded, and lands directly at its offset in the concatenated vertex / face arrays
+    on `dst` (no padded gather of world x max-size, no torch.cat afterwards; a rank's top-plane table is only sent if
+    a slab above it needs it).  With ``merged=True`` the result on `dst` is (all_verts, all_faces, counts, tops) --
+    what merge_gathered() consumes -- instead of the per-rank views."""
     import torch
     dist = _dist()
     verts = verts.reshape(-1, 3).to(torch.float32).contiguous()
     faces = faces.reshape(-1, 3).to(torch.int32).contiguous()
     top = top.reshape(-1).to(torch.int32).contiguous()
     if dist is None or dist.get_world_size(group) == 1:
+        if merged:
+            return verts, faces, [(verts.shape[0], faces.shape[0], top.shape[0])], [top]
         return [(verts, faces, top)]
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     dev = verts.device
-    counts = torch.tensor([verts.shape[0], faces.shape[0], top.shape[0]], dtype=torch.int64, device=dev)
-    all_counts = [torch.zeros_like(counts) for _ in range(world)]
-    dist.all_gather(all_counts, counts, group=group)
-    all_counts = torch.stack(all_counts).cpu().tolist()
-    sizes = [3 * v + 3 * f + t for v, f, t in all_counts]
-    buf = torch.zeros(max(max(sizes), 1), dtype=torch.int32, device=dev)
-    nv3, nf3 = 3 * verts.shape[0], 3 * faces.shape[0]
-    buf[:nv3] = verts.reshape(-1).view(torch.int32)
-    buf[nv3:nv3 + nf3] = faces.reshape(-1)
-    buf[nv3 + nf3:nv3 + nf3 + top.shape[0]] = top
-    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, bufs, dst=dst, group=group)
+    all_counts = _exchange_counts(verts, faces, top, group)
+    # a top-plane table is only needed by the slab above, and only if this slab created vertices at all (a seam
+    # reference points at a vertex the lower slab owns)
+    needs_top = [r < world - 1 and all_counts[r][0] > 0 and all_counts[r][2] > 0 for r in range(world)]
+    peer = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
     if rank != dst:
+        ops = []
+        if verts.shape[0]:
+            ops.append(dist.P2POp(dist.isend, verts, peer(dst), group))
+        if faces.shape[0]:
+            ops.append(dist.P2POp(dist.isend, faces, peer(dst), group))
+        if needs_top[rank]:
+            ops.append(dist.P2POp(dist.isend, top, peer(dst), group))
+        for req in (dist.batch_isend_irecv(ops) if ops else []):
+            req.wait()
         return None
-    out = []
-    for (v, f, t), b in zip(all_counts, bufs):
-        out.append((b[:3 * v].view(torch.float32).reshape(v, 3), b[3 * v:3 * v + 3 * f].reshape(f, 3),
-                    b[3 * v + 3 * f:3 * v + 3 * f + t]))
-    return out
+    tot_v = sum(c[0] for c in all_counts)
+    tot_f = sum(c[1] for c in all_counts)
+    all_v = torch.empty((tot_v, 3), dtype=torch.float32, device=dev)
+    all_f = torch.empty((tot_f, 3), dtype=torch.int32, device=dev)
+    tops, ops, views = [], [], []
+    vo = fo = 0
+    for r, (nv, nf, nt) in enumerate(all_counts):
+        v_view, f_view = all_v[vo:vo + nv], all_f[fo:fo + nf]
+        t_buf = top if r == rank else (torch.empty(nt, dtype=torch.int32, device=dev) if needs_top[r] else None)
+        if r == rank:
+            v_view.copy_(verts)
+            f_view.copy_(faces)
+        else:
+            if nv:
+                ops.append(dist.P2POp(dist.irecv, v_view, peer(r), group))
+            if nf:
+                ops.append(dist.P2POp(dist.irecv, f_view, peer(r), group))
+            if needs_top[r]:
+                ops.append(dist.P2POp(dist.irecv, t_buf, peer(r), group))
+        tops.append(t_buf)
+        views.append((v_view, f_view, t_buf))
+        vo += nv
+        fo += nf
+    for req in (dist.batch_isend_irecv(ops) if ops else []):
+        req.wait()
+    if merged:
+        return all_v, all_f, all_counts, tops
+    return views
+
+
+def merge_gathered(all_v, all_f, counts, tops):
+    """In-place version of merge_fragments for the arrays gather_fragments(merged=True) returns: the faces of slab k
+    get the exclusive scan of the vertex counts added, its seam references are resolved through the top-plane
+    table of the slab below.  -> (verts, faces) with exactly the ids of the single sweep.  One host
+    synchronisation (the consistency flag) for the whole merge."""
+    import torch
+    fo = vo = 0
+    prev_top, prev_vo = None, 0
+    bad = torch.zeros((), dtype=torch.bool, device=all_f.device)
+    for k, (nv, nf, _) in enumerate(counts):
+        f = all_f[fo:fo + nf]
+        if k > 0 and nf:
+            seam = f < -1
+            if prev_top is None:
+                bad |= seam.any()
+                f += vo
+            else:
+                ids = prev_top.to(torch.int64)[(-2 - f.to(torch.int64)).clamp_(min=0, max=prev_top.numel() - 1)]
+                bad |= (seam & (ids < 0)).any()
+                f.copy_(torch.where(seam, ids + prev_vo, f.to(torch.int64) + vo).to(torch.int32))
+        prev_top, prev_vo = tops[k], vo
+        vo += nv
+        fo += nf
+    if bool(bad):
+        raise RuntimeError("a slab references a seam edge the slab below never created")
+    return all_v, all_f
 
 
 def merge_fragments(frags):
@@ -136,11 +206,11 @@ def slab_fragment(vec, decoder, use_net, sigmoid, level, dims, padding, z_lo, z_
     if n0 < 2:  # a rank without cell layers contributes nothing
         return (torch.empty((0, 3), dtype=torch.float32, device=dev), torch.empty((0, 3), dtype=torch.int32, device=dev),
                 torch.full((plane * 3,), -1, dtype=torch.int32, device=dev), mm)
-    w = R._work_for(dev.index)
     nv, nf = ctypes.c_int64(), ctypes.c_int64()
     L = _lib.lib()
     with torch.cuda.device(dev):
         st = _lib.stream_ptr()
+        w = R._work_for(dev.index, st)
         _lib.check(L.dj_mc_count(w.handle, vol.data_ptr(), n0, d1, d2, int(z_lo), int(bool(seam)), float(level), 0,
                                  ctypes.byref(nv), ctypes.byref(nf), st))
         verts = torch.empty((nv.value, 3), device=dev, dtype=torch.float32)
@@ -194,8 +264,8 @@ def create_mesh_sharded(vec, decoder, use_net, sigmoid=True, level=0.5, gradient
         raise errors.IsosurfaceExtractionError("Surface level must be within volume data range.")
     if most == 0:
         raise errors.IsosurfaceExtractionError("No surface found at the given iso value.")
-    frags = gather_fragments(verts, faces, top, group=group, dst=dst)
-    if frags is None:
+    got = gather_fragments(verts, faces, top, group=group, dst=dst, merged=True)
+    if got is None:
         return None
-    v, f = merge_fragments(frags)
+    v, f = merge_gathered(*got)
     return finish_mesh(v, f, dims, padding, gradient_direction)

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DJ_ABI_VERSION 2
+#define DJ_ABI_VERSION 3
 
 /* status codes */
 #define DJ_OK 0
@@ -176,6 +176,16 @@ int dj_host_write_obj(const char* path, const double* verts, int64_t nv, const i
  * RandomState.permutation(n) -- arange(n) shuffled by mtrand's _shuffle_raw / random_interval -- continuing the
  * MT19937 state (key624, *pos) as np.random.get_state() returns it; *pos is updated.  out [n] int64.  No GPU. */
 int dj_host_mt19937_permutation(uint32_t* key624, int32_t* pos, int64_t n, int64_t* out);
+
+/* replaces: the per-iteration `core.data.select_samples(pts, values, num_samples, uniform_ratio)` of the latent loop
+ * (reconstruct.py:114-118 -> core/data.py:15-73,122-176) for ALL iterations of one reconstruct() call, host side, on
+ * numpy's global MT19937 stream: out [num_iterations][num_samples] int32 row indices, bit-identical to calling the
+ * reference sampler num_iterations times from the state (key624, *pos) (np.random.get_state()); *pos / key624 are
+ * left where numpy would be.  sdf [n_pts] float32 (one value column).  The calling thread walks the generator,
+ * n_threads workers (0 = host cores - 1) finish the shuffles.  DJ_ERR_NO_SAMPLES where the reference raises
+ * NoSamplesError.  No GPU. */
+int dj_host_sample_schedule(uint32_t* key624, int32_t* pos, const float* sdf, int64_t n_pts, double uniform_ratio,
+                            int num_iterations, int num_samples, int n_threads, int32_t* out);
 
 /* replaces: core.data.select_samples(pts, values, num_samples, uniform_ratio)
  * (core/data.py:15-73,122-176) for every iteration at once, on the device, from a counter

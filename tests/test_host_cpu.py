@@ -116,6 +116,54 @@ def test_library_permutation_continues_numpys_legacy_stream():
     assert np.array_equal(c1, data._permutation(250000)[:62500])
 
 
+@pytest.mark.parametrize("n_pts,iters,num_samples,ratio,seed", [
+    (500000, 4, 30000, 0.2, 0),   # the reference's sizes: 250 k surface + 250 k uniform rows, 30,000 per batch
+    (120001, 5, 8000, 0.5, 1),    # no ratio step, odd pool
+    (90000, 3, 8001, 0.7, 2),     # surface rows sub-sampled, odd batch
+    (4001, 5, 6000, 0.2, 3),      # fewer rows of a class than asked for: drawn with replacement
+    (70000, 3, 1, 0.3, 4),        # one sample per batch (no positive window at all)
+])
+def test_native_schedule_is_the_reference_sampler_on_numpys_stream(n_pts, iters, num_samples, ratio, seed):
+    """dj_host_sample_schedule (all iterations in one native call, threaded) == calling the reference-pinned Python
+    sampler once per iteration: same rows, and numpy's global generator is left exactly where it would be."""
+    import synth_data
+    from deepjoin_b200 import reconstruct as R
+    sdf = synth_data.make_sample_set(n_pts, seed=seed)[1].reshape(-1)
+    np.random.seed(seed)
+    np.random.randn()  # a cached gaussian and a mid-block position
+    a = R.make_schedule(sdf, iters, num_samples, ratio)
+    tail_a = (np.random.randint(1 << 30), np.random.randn())
+    os.environ["DEEPJOIN_B200_PY_SAMPLER"] = "1"
+    try:
+        np.random.seed(seed)
+        np.random.randn()
+        b = R.make_schedule(sdf, iters, num_samples, ratio)
+        tail_b = (np.random.randint(1 << 30), np.random.randn())
+    finally:
+        del os.environ["DEEPJOIN_B200_PY_SAMPLER"]
+    assert a.dtype == np.int32 and np.array_equal(a, b) and tail_a == tail_b
+
+
+def test_native_schedule_matches_the_reference_made_fixture():
+    """... and directly against rows the reference's own select_samples produced (tests/golden/sampler.npz)."""
+    from deepjoin_b200 import reconstruct as R
+    g = np.load(os.path.join(G, "sampler.npz"))
+    pts = np.hstack((g["xyz"], g["n"]))
+    for seed, n, key in ((11, 600, "sel"), (12, 601, "sel2")):
+        np.random.seed(seed)
+        idx = R.make_schedule(g["sdf"], 1, n, 0.2)[0]
+        assert np.array_equal(pts[idx], g[key + "_pts"]) and np.array_equal(g["sdf"][idx], g[key + "_vals"])
+
+
+def test_native_schedule_raises_no_samples_error():
+    from deepjoin_b200 import reconstruct as R
+    from deepjoin_b200.core import errors
+    with pytest.raises(errors.NoSamplesError):
+        R.make_schedule(np.full(1000, 0.5, np.float32), 2, 100, 0.2)
+    with pytest.raises(errors.NoSamplesError):
+        R.make_schedule(np.full(1000, -0.5, np.float32), 2, 100, 0.2)
+
+
 @pytest.mark.parametrize("kind", ["default", "trained_norm"])
 def test_surface_interior_schedule_reproduces_the_reference_run(kind):
     """sampling_method="surface_interior_only" (reconstruct.py:60-98): the host schedule, fed to the oracle's Adam loop,

@@ -63,14 +63,18 @@ def _worker(rank, world, port, out_path):
         mine = torch.tensor(list(P.shard_items(10, world, rank)), dtype=torch.int64)
         sizes = [torch.zeros(1, dtype=torch.int64) for _ in range(world)]
         dist.all_gather(sizes, torch.tensor([len(mine)]))
+        got = P.gather_fragments(torch.from_numpy(v), torch.from_numpy(f), torch.from_numpy(top), dst=0, merged=True)
         if rank == 0:
             assert frags is not None and len(frags) == world
-            mv, mf = P.merge_fragments(frags)
+            mv, mf = P.merge_fragments([(a, b, c if c is not None else torch.zeros(0, dtype=torch.int32)) for a, b, c in frags])
+            gv, gf = P.merge_gathered(*got)  # the path create_mesh_sharded takes: merged in place
+            assert torch.equal(gv, mv) and torch.equal(gf, mf)
+            assert got[3][-1] is None  # the last slab's top-plane table is never sent
             mesh = P.finish_mesh(mv, mf, vol.shape, 0.1, "descent")
             np.savez(out_path, v=mv.numpy(), f=mf.numpy(), mesh_v=mesh.vertices, mesh_f=mesh.faces,
                      sizes=np.array([int(s) for s in sizes]))
         else:
-            assert frags is None
+            assert frags is None and got is None
     finally:
         dist.destroy_process_group()
 
