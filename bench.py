@@ -7,15 +7,25 @@ decoder (use_net=1: B = max(C, -T), both MLPs) + marching cubes; with N > 1 ever
 shape (independent shapes shard with no data-path collective -> weak scaling).
 A step = one grid query + one marching-cubes extraction.
 
+The headline is measured in the PARITY mode, precision "fp16x2" (split-operand tensor-core kernel: 2.7e-5 max SDF
+error against the fp64 decoder on the trained-norm weights used here; north star 1e-3).  The single-pass bf16 kernel
+-- 4x the throughput, but 5e-2 max SDF error on these weights, i.e. NOT within the stated tolerance -- is reported
+next to it under "throughput_mode", never as the headline.
+
   value     queries/s with everything resident in HBM (device-timed, max over ranks)
   e2e       the same through core.reconstruct.create_mesh (host code in, host vertices/faces out)
-  roofline  tensor-core bound of the fused decoder kernel: algorithmic FLOP (5,518,336 / query,
-            SURVEY.md 8d) / CUDA-event time of the grid-query launches
-  cpu_baseline  the oracle's torch-fp32 restatement of the reference decoder on the host cores,
-            bounded sample (rank 0, N=1)
+  roofline  tensor-core bound of the fused decoder kernel: USEFUL algorithmic FLOP (5,518,336 / query)
+            / CUDA-event time of the grid-query launches; "tensor_busy_frac" counts the 4 partial products the
+            split-operand mode issues per useful one
+  latent    configs[2]: through reconstruct() (the reference's call surface, reference-exact sampler) and through
+            optimize_codes (all shapes of a rank per launch, device sampler)
+  slab      configs[3]: ONE 512^3 grid sharded by axis-0 slabs over the ranks, fragments gathered over NCCL
+  cpu_baseline  the oracle's torch-fp32 restatement of the reference decoder on the host cores (bounded sample,
+            rank 0, N=1), plus the reference's latent Adam iteration (B3) and a CPU marching-cubes sweep (B5)
 
 `--impl reference` times that CPU path alone (the reference is pure Python/PyTorch; its CPU
 implementation of the path is what oracle/decoder_oracle.py restates and pins).
+`--sweep` prints BASELINE configs[4] (point-query throughput 2^20 .. 2^30, CodeLength 128 / 256, every precision).
 """
 import argparse
 import json
@@ -119,6 +129,44 @@ def cpu_decoder_rate(n_points, use_net=1, threads=None):
     return done / dt, done, dt, torch.get_num_threads()
 
 
+def cpu_latent_iteration(n_iter=4, n_samples=30000):
+    """B3: the reference's latent Adam iteration (reconstruct.py:107-226: sampler + forward + autograd
+    backward + Adam) restated by the oracle, torch fp32 on the host cores: seconds per iteration."""
+    import numpy as np
+    import torch
+    import synth_data
+    from oracle import decoder_oracle as O
+    net = O.fold(synth_data.make_state_dict(0, "trained_norm"), dtype=torch.float32)
+    xyz, sdf, nrm = synth_data.make_sample_set(500000, seed=0)
+    pts = np.hstack((xyz, nrm))
+    torch.manual_seed(0)
+    np.random.seed(0)
+    code0 = torch.cat([torch.ones(1, 128).normal_(0, 0.01), torch.ones(1, 64).normal_(0, 0.01)], 1)
+
+    def batches(e):
+        p, v = O.select_samples(pts, sdf, n_samples, uniform_ratio=0.2)
+        f = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32))
+        return f(p[:, :3]), f(v), f(p[:, 3:])
+    O.adam_loop(net, code0, batches, 2, lr=5e-3)  # warm-up
+    t0 = time.perf_counter()
+    O.adam_loop(net, code0, batches, n_iter, lr=5e-3)
+    return (time.perf_counter() - t0) / n_iter
+
+
+def cpu_marching_cubes_ms(volume):
+    """B5: the CPU sweep (oracle/mc_oracle.c, single thread -- skimage's is single-threaded Cython too) on the same volume."""
+    from oracle import mc_oracle
+    mc_oracle.lib()  # build / load / table set-up outside the timed region
+    t0 = time.perf_counter()
+    v, f = mc_oracle.marching_cubes(volume, 0.0, "ascent")
+    return 1e3 * (time.perf_counter() - t0), len(v), len(f)
+
+
+def run_sweep(args):
+    import subprocess
+    sys.exit(subprocess.call([sys.executable, os.path.join(ROOT, "tools", "sweep.py"), "--max-log2", str(args.sweep_max_log2)]))
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,18 +208,24 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dims", type=int, default=256)
     ap.add_argument("--use-net", type=int, default=1)
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp16", "fp32"])
+    ap.add_argument("--precision", default="fp16x2", choices=["fp16x2", "bf16", "fp16", "fp32"],
+                    help="headline precision; fp16x2 = the parity mode (default).  bf16 is always reported as throughput_mode")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE configs[4]: point-query throughput sweep (tools/sweep.py)")
+    ap.add_argument("--sweep-max-log2", type=int, default=26)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--query-only", action="store_true", help="diagnostics: time the grid query alone (not a bench line)")
     ap.add_argument("--latent-shapes", type=int, default=8,
                     help="shapes per GPU of the second half of the metric (BASELINE configs[2]: 800 Adam iterations x 30,000 "
                          "samples per shape, then one 256^3 restoration mesh); 0 disables")
-    ap.add_argument("--slab-dims", type=int, default=0,
-                    help="also time BASELINE configs[3]: ONE grid of this size sharded by axis-0 slabs over the ranks, "
-                         "fragments gathered to rank 0 over NCCL (adds a 'slab' object to the JSON line)")
+    ap.add_argument("--slab-dims", type=int, default=512,
+                    help="BASELINE configs[3]: ONE grid of this size sharded by axis-0 slabs over the ranks, fragments "
+                         "gathered to rank 0 over NCCL ('slab' object of the JSON line; at N=1 the single-GPU reference "
+                         "point of the strong-scaling curve); 0 disables")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.sweep:
+        return run_sweep(args)
 
     import numpy as np
     import torch
@@ -203,65 +257,106 @@ def main():
     code_dev = code.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def device_step(ev=None):
-        flush.fill_(1)
-        if ev:
-            ev[0].record()
-        vol = R.decode_shape_device(code_dev, dec, dims, use_net=u, padding=0.1, sigmoid=False)
-        if ev:
-            ev[1].record()
-        if args.query_only:
+    def timed_steps(decoder, steps, warm):
+        """`steps` device steps (L2 flush, grid query, marching cubes), CUDA events on the launching stream.
+        -> (total ms incl. flushes, mean query ms, mean MC ms, vertices, faces, launches, last volume)"""
+        def device_step(ev=None):
+            flush.fill_(1)
+            if ev:
+                ev[0].record()
+            vol = R.decode_shape_device(code_dev, decoder, dims, use_net=u, padding=0.1, sigmoid=False)
+            if ev:
+                ev[1].record()
+            if args.query_only:
+                if ev:
+                    ev[2].record()
+                return vol, vol, vol
+            v, f = R.marching_cubes(vol.reshape(dims), 0.0, "ascent")
             if ev:
                 ev[2].record()
-            return vol, vol
-        v, f = R.marching_cubes(vol.reshape(dims), 0.0, "ascent")
-        if ev:
-            ev[2].record()
-        return v, f
+            return v, f, vol
+        for _ in range(warm):
+            v, f, vol = device_step()
+        barrier()
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+        _lib.lib().dj_launch_count(1)
+        barrier()
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for s_ in range(steps):
+            v, f, vol = device_step(evs[s_])
+        t1.record()
+        barrier()
+        launches = int(_lib.lib().dj_launch_count(0))
+        return (t0.elapsed_time(t1), sum(e[0].elapsed_time(e[1]) for e in evs) / steps,
+                sum(e[1].elapsed_time(e[2]) for e in evs) / steps, int(v.shape[0]), int(f.shape[0]), launches, vol)
 
-    for _ in range(max(args.warmup, 3)):
-        v, f = device_step()
-    barrier()
+    def timed_e2e(decoder, steps):
+        for _ in range(2):
+            mesh = R.create_mesh(code, decoder, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
+        barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            mesh = R.create_mesh(code, decoder, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
+        torch.cuda.synchronize()
+        return 1e3 * (time.perf_counter() - w0), mesh
+
+    def allmax(*vals):
+        t = torch.tensor(list(vals), dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    _lib.lib().dj_launch_count(1)
-    barrier()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    for s in range(args.steps):
-        v, f = device_step(evs[s])
-    t1.record()
-    barrier()
-    launches = int(_lib.lib().dj_launch_count(0))
-    ms = t0.elapsed_time(t1)
-    q_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
-    mc_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
-    nv, nf = int(v.shape[0]), int(f.shape[0])
+    ms, q_ms, mc_ms, nv, nf, launches, vol_last = timed_steps(dec, args.steps, max(args.warmup, 3))
 
     if args.query_only:
         if rank == 0:
-            print(json.dumps({"diagnostic": "query-only", "grid_query_ms": q_ms, "queries_per_s": npts / (q_ms * 1e-3),
+            print(json.dumps({"diagnostic": "query-only", "precision": args.precision, "grid_query_ms": q_ms,
+                              "queries_per_s": npts / (q_ms * 1e-3),
                               "tflops_alg": npts * FLOP_ALG[u] / (q_ms * 1e-3) / 1e12, "clocks": sampler.stop()}))
         return
     # ---- end to end through the public API: host code in, host mesh out
-    for _ in range(2):
-        mesh = R.create_mesh(code, dec, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(args.steps):
-        mesh = R.create_mesh(code, dec, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims, padding=0.1)
-    torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - w0)
+    e2e_ms, mesh = timed_e2e(dec, args.steps)
     clocks = sampler.stop() if sampler else None
+    vol_host = vol_last.reshape(dims).cpu().numpy() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+
+    # ---- the single-pass bf16 kernel on the same workload: 4x the throughput, OUTSIDE the stated tolerance
+    throughput = None
+    if args.precision != "bf16":
+        dec_bf = make_decoder(rank % 8, dev, "bf16")
+        b_ms, bq_ms, bmc_ms, bnv, bnf, _, _ = timed_steps(dec_bf, args.steps, 3)
+        be2e_ms, bmesh = timed_e2e(dec_bf, args.steps)
+        b_ms, be2e_ms = allmax(b_ms, be2e_ms)
+        throughput = (b_ms, bq_ms, bmc_ms, bnv, bnf, be2e_ms)
+        del dec_bf
 
     latent = None
-    if args.latent_shapes and not args.query_only:
+    if args.latent_shapes:
         from deepjoin_b200 import reconstruct as RR
         n_sh, iters_l, ns_l = args.latent_shapes, 800, 30000
+        lat_prec = args.precision
+        # (a) the reference's call surface: reconstruct(decoder, ..., test_sdf=(xyz, sdf, n) host arrays of 500,000 rows
+        # as process_sample.py / process_sdf2.py store them) with its own sampler on numpy's stream, one shape
+        xyz_r, sdf_r, nrm_r = synth_data.make_sample_set(500000, seed=rank)
+        np.random.seed(rank)
+        torch.manual_seed(rank)
+        RR.reconstruct(dec, 20, 128, 64, (xyz_r, sdf_r, nrm_r), 0.01, 1.0, 0.0, 1.0, 0.1, num_samples=ns_l, lr=5e-3, l2reg=True)
+        barrier()
+        w_r = time.perf_counter()
+        loss_r, code_r = RR.reconstruct(dec, iters_l, 128, 64, (xyz_r, sdf_r, nrm_r), 0.01, 1.0, 0.0, 1.0, 0.1,
+                                        num_samples=ns_l, lr=5e-3, l2reg=True)
+        torch.cuda.synchronize()
+        rec_s = time.perf_counter() - w_r
+        w_s = time.perf_counter()
+        RR.make_schedule(sdf_r, iters_l, ns_l, 0.2)
+        sched_s = time.perf_counter() - w_s
+        del xyz_r, nrm_r
+        # (b) the batched extension: all shapes of the rank in one fused launch per iteration, device sampler
         pools = []
         for sh in range(n_sh):  # every shape its own synthetic fractured-mug sample set (resident in HBM)
             xyz_s, sdf_s, nrm_s = synth_data.make_sample_set(100000, seed=rank * n_sh + sh)
@@ -286,7 +381,7 @@ def main():
             t_b = torch.cuda.Event(enable_timing=True)
             t_a.record()
             logs, codes = RR.optimize_codes(dec, torch.cat(codes0), pools, sched[:, :n_it], 5e-3, 1.0, 1.0, 0.1, l2reg=True,
-                                            code_reg_lambda=1e-4, precision=args.precision)
+                                            code_reg_lambda=1e-4, precision=lat_prec)
             t_b.record()
             torch.cuda.synchronize()
             run_shapes.opt_ms = t_a.elapsed_time(t_b)
@@ -309,78 +404,98 @@ def main():
         logs, n_mesh = run_shapes(iters_l)
         l1.record()
         torch.cuda.synchronize()
-        tl = torch.tensor([l0.elapsed_time(l1)], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        tl, rec_max = allmax(l0.elapsed_time(l1), rec_s)
         if rank == 0:
             latent = {"workload": "configs[2]: %d shapes per GPU x %d Adam iterations x %d samples (device sampler, all shapes of a "
                                   "rank in one fused forward+backward tensor-core launch per iteration), then one %d^3 restoration "
-                                  "mesh per shape" % (n_sh, iters_l, ns_l, d),
-                      "shapes_per_s": world * n_sh / (float(tl[0]) * 1e-3), "ms_per_shape": float(tl[0]) / n_sh,
+                                  "mesh per shape (meshes in precision %s)" % (n_sh, iters_l, ns_l, d, args.precision),
+                      "shapes_per_s": world * n_sh / (tl * 1e-3), "ms_per_shape": tl / n_sh,
                       "wall_ms_per_shape": 1e3 * (time.perf_counter() - wl) / n_sh, "meshes_with_surface": n_mesh,
                       "adam_loop_ms_per_shape": run_shapes.opt_ms / n_sh, "schedule_ms_per_shape": run_shapes.sched_ms / n_sh,
                       "mesh_ms_per_shape": run_shapes.mesh_ms / n_sh,
                       "adam_loop_tflops_alg": n_sh * iters_l * ns_l * 11.03e6 / (run_shapes.opt_ms * 1e-3) / 1e12,
-                      "loss_first_last_shape0": [float(logs[0, 0, 1]), float(logs[0, -1, 1])], "precision": args.precision}
+                      "loss_first_last_shape0": [float(logs[0, 0, 1]), float(logs[0, -1, 1])], "precision": lat_prec,
+                      "reconstruct_api": {
+                          "what": "deepjoin_b200.reconstruct.reconstruct(decoder, 800, 128, 64, (xyz, sdf, n) host arrays of "
+                                  "500,000 rows, ..., num_samples=30000): the reference's call surface and its own sampler "
+                                  "(numpy stream, bit-identical batches), one shape per call",
+                          "s_per_shape": rec_max, "shapes_per_s": world / rec_max, "host_sampler_s": sched_s,
+                          "loss_first_last": [float(loss_r["loss"][0]), float(loss_r["loss"][-1])]}}
     slab = None
     if args.slab_dims:
         from deepjoin_b200 import parallel as Par
         sd = (args.slab_dims,) * 3
-        dec0 = make_decoder(0, dev, args.precision)  # same weights on every rank
-        code0 = synth_data.trained_code(0).to(dev)
-        for _ in range(2):
-            m = Par.create_mesh_sharded(code0, dec0, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=sd, padding=0.1)
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        s0.record()
-        reps = 3
-        for _ in range(reps):
+        slab = {"workload": "configs[3]: %d^3 grid sharded by axis-0 slabs over %d GPU(s), exact-size grouped NCCL send/recv of "
+                            "mesh fragments into the merged arrays, mesh finished on rank 0 (host Mesh out); scaling: strong"
+                            % (args.slab_dims, world), "n_gpus": world}
+        for prec in ([args.precision] if args.precision == "bf16" else [args.precision, "bf16"]):
+            dec0 = make_decoder(0, dev, prec)  # same weights on every rank
+            code0 = synth_data.trained_code(0).to(dev)
             m = Par.create_mesh_sharded(code0, dec0, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=sd, padding=0.1)
             barrier()
-        s1.record()
-        torch.cuda.synchronize()
-        ts = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(ts, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            slab = {"workload": "configs[3]: %d^3 grid sharded by axis-0 slabs over %d GPU(s), NCCL gather of mesh fragments, "
-                                "mesh finished on rank 0 (host Mesh out)" % (args.slab_dims, world),
-                    "ms_per_mesh": float(ts[0]), "wall_ms_per_mesh": 1e3 * (time.perf_counter() - w0) / reps,
-                    "queries_per_s": args.slab_dims ** 3 / (float(ts[0]) * 1e-3),
-                    "vertices": int(len(m.vertices)), "faces": int(len(m.faces))}
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, e2e_ms = float(t[0]), float(t[1])
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            s0.record()
+            reps = 2
+            for _ in range(reps):
+                m = Par.create_mesh_sharded(code0, dec0, u, sigmoid=False, level=0.0, gradient_direction="ascent", dims=sd, padding=0.1)
+                barrier()
+            s1.record()
+            torch.cuda.synchronize()
+            (ts,) = allmax(s0.elapsed_time(s1) / reps)
+            if rank == 0:
+                slab[prec] = {"ms_per_mesh": ts, "wall_ms_per_mesh": 1e3 * (time.perf_counter() - w0) / reps,
+                              "queries_per_s": args.slab_dims ** 3 / (ts * 1e-3),
+                              "vertices": int(len(m.vertices)), "faces": int(len(m.faces))}
+            del dec0, m
+    ms, e2e_ms = allmax(ms, e2e_ms)
     if rank == 0:
         burst, sustained, hbm, which = peaks()
         value = world * npts * args.steps / (ms * 1e-3)
-        achieved = npts * FLOP_ALG[u] / (q_ms * 1e-3) / 1e12
         peak = sustained
+        mma_mult = 4 if args.precision == "fp16x2" else 1
+
+        def roof(q_ms_, mult, prec):
+            achieved = npts * FLOP_ALG[u] / (q_ms_ * 1e-3) / 1e12
+            r = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                 "traffic": None, "kernel": "tc2_forward_kernel<%s>" % prec if prec != "fp32" else "sgemm_kernel",
+                 "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step); burst %.1f" % (which, burst),
+                 "flop_per_query": FLOP_ALG[u], "mma_flop_issued_per_useful_flop": mult,
+                 "tensor_busy_frac": mult * achieved / peak}
+            if prec == "bf16" and d == 256:
+                # dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 launch (profiles/r01_tc2_forward_256_ncu_full.txt)
+                r["traffic"] = 20361728
+            return r
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32"}[args.precision], "data": "synthetic",
+            "vs_baseline": None, "dtype": {"bf16": "bf16", "fp16": "f16", "fp32": "f32", "fp16x2": "f16x2 (split operands, fp32 accumulate)"}[args.precision],
+            "data": "synthetic",
             "config": {"workload": "configs[1]: single-shape dense query + marching cubes at %d^3 grid per GPU, "
                                    "use_net=%d, padding 0.1, level 0 ascent; synthetic trained-norm weights" % (d, u),
                        "l2": "256 MB flush buffer written before every step (inside the timed bracket)",
                        "grid_query_ms": q_ms, "marching_cubes_ms": mc_ms, "vertices": nv, "faces": nf,
-                       "precision": args.precision},
+                       "precision": args.precision,
+                       "parity": {"fp16x2": "max |dSDF| 2.7e-5 vs the fp64 decoder on these weights (tests/test_gpu_forward.py), north star 1e-3",
+                                  "bf16": "max |dSDF| 5e-2 on these weights: OUTSIDE the stated tolerance (throughput mode only)",
+                                  "fp16": "max |dSDF| 9e-3 on these weights: outside the stated tolerance",
+                                  "fp32": "max |dSDF| 1.5e-5 (CUDA-core path)"}[args.precision]},
             "e2e": {"value": world * npts * args.steps / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": int(code.numel() * 4), "d2h_bytes_per_step": int(mesh.vertices.nbytes + mesh.faces.nbytes),
                     "ms_per_step": e2e_ms / args.steps, "api": "deepjoin_b200.core.reconstruct.create_mesh"},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 launch (ncu --set full,
-                         # profiles/r01_tc2_forward_256_ncu_full.txt): 6.3 MB of weights + 14.0 MB of the 67 MB
-                         # output volume (the rest is still in L2 when the kernel ends)
-                         "traffic": 20361728 if (args.precision != "fp32" and d == 256) else None,
-                         "kernel": "tc2_forward_kernel" if args.precision != "fp32" else "sgemm_kernel",
-                         "peak_source": "bf16_tflops_sustained of %s (kernel timed inside a long step); burst %.1f" % (which, burst),
-                         "flop_per_query": FLOP_ALG[u]},
+            "roofline": roof(q_ms, mma_mult, args.precision),
             "clocks": clocks,
         }
+        if throughput:
+            b_ms, bq_ms, bmc_ms, bnv, bnf, be2e_ms = throughput
+            line["throughput_mode"] = {
+                "precision": "bf16", "note": "single-pass bf16 operands: max |dSDF| 5e-2 on these weights -- outside the 1e-3 "
+                                             "tolerance, reported for the roofline, not as the headline",
+                "value": world * npts * args.steps / (b_ms * 1e-3), "unit": "queries/s", "ms_per_step": b_ms / args.steps,
+                "grid_query_ms": bq_ms, "marching_cubes_ms": bmc_ms, "vertices": bnv, "faces": bnf,
+                "e2e": {"value": world * npts * args.steps / (be2e_ms * 1e-3), "unit": "queries/s", "ms_per_step": be2e_ms / args.steps},
+                "roofline": roof(bq_ms, 1, "bf16")}
         if latent:
             line["latent"] = latent
         if slab:
@@ -390,6 +505,19 @@ def main():
             line["cpu_baseline"] = {"value": rate, "unit": "queries/s", "cores": thr, "kind": "port",
                                     "sample": "%d points (%.1f s), torch fp32 restatement of the reference Decoder.forward, "
                                               "use_net=%d" % (done, dt, u)}
+            try:
+                s_it = cpu_latent_iteration()
+                line["cpu_baseline"]["latent_s_per_iteration"] = s_it
+                line["cpu_baseline"]["latent_sample"] = ("B3: 4 iterations of the reference's latent loop (reconstruct.py:107-226: numpy "
+                                                         "sampler over 500,000 rows, 30,000-sample forward + autograd backward, Adam), "
+                                                         "oracle port, %d threads; x800 iterations = %.0f s per shape" % (thr, 800 * s_it))
+                mc_cpu_ms, cv, cf = cpu_marching_cubes_ms(vol_host)
+                line["cpu_baseline"]["marching_cubes_ms"] = mc_cpu_ms
+                line["cpu_baseline"]["marching_cubes_sample"] = ("B5: the %d^3 volume of this run, oracle/mc_oracle.c sweep, 1 thread "
+                                                                 "(%d vertices, %d faces; skimage's Lewiner sweep is single-threaded Cython)"
+                                                                 % (d, cv, cf))
+            except Exception as e:  # noqa: BLE001 -- the extra baselines must not cost the headline line
+                line["cpu_baseline"]["extra_baselines_error"] = repr(e)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

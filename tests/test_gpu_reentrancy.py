@@ -36,7 +36,9 @@ def test_two_host_threads_mesh_with_one_decoder():
     dec = util.make_decoder(0, "trained_norm", precision="fp16x2")
     codes = [util.trained_code(i) for i in range(4)]
     dims = (48, 48, 48)
-    serial = [R.create_mesh(c, dec, 1, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims) for c in codes]
+    # the synthetic weights are centred on latent row 0 only: take every code's own median value as its level
+    levels = [float(np.median(R.decode_shape(c, dec, dims, use_net=1, padding=0.1, reshape=False, sigmoid=False))) for c in codes]
+    serial = [R.create_mesh(c, dec, 1, sigmoid=False, level=lv, gradient_direction="ascent", dims=dims) for c, lv in zip(codes, levels)]
     pts = synth.make_points(50_000, 3).numpy().astype(np.float64)
     serial_vals = [R.decode_samples(c, dec, pts, use_net=1, sigmoid=False) for c in codes]
     results, values, errs = [None] * 4, [None] * 4, []
@@ -45,7 +47,7 @@ def test_two_host_threads_mesh_with_one_decoder():
         try:
             torch.cuda.set_device(0)
             for _ in range(5):
-                results[i] = R.create_mesh(codes[i], dec, 1, sigmoid=False, level=0.0, gradient_direction="ascent", dims=dims)
+                results[i] = R.create_mesh(codes[i], dec, 1, sigmoid=False, level=levels[i], gradient_direction="ascent", dims=dims)
                 values[i] = R.decode_samples(codes[i], dec, pts, use_net=1, sigmoid=False)
         except Exception as e:  # noqa: BLE001
             errs.append(e)

@@ -32,7 +32,10 @@ def main():
         for log2 in range(20, args.max_log2 + 1, 2):
             n = 1 << log2
             pts = torch.rand((n, 3), device=dev) * 1.2 - 0.6
-            for precision in ("bf16", "fp16", "fp32"):  # fp16: tf32's 10-bit mantissa at the bf16 rate
+            # fp16x2: the parity mode (split operands).  fp16: IEEE half = tf32's 10-bit mantissa at the bf16 rate; a
+            # kind::tf32 instantiation of the fused kernel does not exist (4-byte operands: a 128-row layer input is
+            # 256 KB, neither shared nor tensor memory holds it next to the accumulators -- DESIGN.md 3.1)
+            for precision in ("fp16x2", "bf16", "fp16", "fp32"):
                 if precision == "fp32" and log2 > args.fp32_max_log2:
                     continue
                 for u in (0, 1):
