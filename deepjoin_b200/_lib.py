@@ -28,7 +28,8 @@ class LatentCfg(ctypes.Structure):
     _fields_ = [("num_iterations", ctypes.c_int32), ("num_samples", ctypes.c_int32), ("lr", c_f), ("lambda1", c_f),
                 ("lambda3", c_f), ("clamp_dist", c_f), ("code_reg_lambda", c_f), ("l2reg", ctypes.c_int32),
                 ("beta1", c_f), ("beta2", c_f), ("eps", c_f), ("log_every", ctypes.c_int32),
-                ("precision", ctypes.c_int32), ("loss_kind", ctypes.c_int32)]
+                ("precision", ctypes.c_int32), ("loss_kind", ctypes.c_int32), ("iter_offset", ctypes.c_int32),
+                ("total_iterations", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes); every symbol include/deepjoin_b200.h declares

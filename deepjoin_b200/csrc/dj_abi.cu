@@ -5,6 +5,7 @@
 #include <cmath>
 #include <condition_variable>
 #include <deque>
+#include <functional>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -64,6 +65,8 @@ struct DjPack {
   uint8_t* lat_stream[2] = {nullptr, nullptr};
   uint8_t* lat_stream_h[2] = {nullptr, nullptr};  // forward tiles in IEEE half
   lat2::Layer lat_prog[lat2::MAX_PROG];
+  lat2::Layer lat_prog_x[lat2::MAX_PROG];   // split-operand program (DJ_PREC_FP16X2): every stage as W_lo and W_hi
+  uint8_t* lat_stream_x[2] = {nullptr, nullptr};
   int lat_n_prog = 0;
   int lat_net1_lo = 0, lat_net1_hi = 0;  // program entries of the second net (forward + backward)
   bool lat_attr_set = false;
@@ -120,6 +123,7 @@ static void free_pack(DjPack* p) {
   for (int r = 0; r < 2; r++) {
     if (p->lat_stream[r]) cudaFree(p->lat_stream[r]);
     if (p->lat_stream_h[r]) cudaFree(p->lat_stream_h[r]);
+    if (p->lat_stream_x[r]) cudaFree(p->lat_stream_x[r]);
   }
   if (p->prof) cudaFree(p->prof);
   for (int i = 0; i < 2; i++) {
@@ -216,6 +220,18 @@ static void pack_tile_T(const float* W, int ldw, int out_real, int in_real, int 
       const int gn = n0 + r, gk = k0 + k;  // gn: input index of the layer (output column of the backward GEMM), gk: its output index
       const float v = (gn < in_real && gk < out_real) ? W[(size_t)gk * ldw + gn] : 0.f;
       const __nv_bfloat16 b = __float2bfloat16_rn(v);
+      const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
+      memcpy(dst + off, &b, 2);
+    }
+}
+// the same, split-operand program: bf16 high part (part 0) or the bf16 rounding remainder (part 1) of the weight
+static void pack_tile_T_x2(const float* W, int ldw, int out_real, int in_real, int n0, int k0, int rows, uint8_t* dst, int part) {
+  for (int r = 0; r < rows; r++)
+    for (int k = 0; k < 64; k++) {
+      const int gn = n0 + r, gk = k0 + k;
+      const float w = (gn < in_real && gk < out_real) ? W[(size_t)gk * ldw + gn] : 0.f;
+      const float hi = __bfloat162float(__float2bfloat16_rn(w));
+      const __nv_bfloat16 b = __float2bfloat16_rn(part == 0 ? hi : w - hi);
       const size_t off = (size_t)r * 128 + (size_t)(((k >> 3) ^ (r & 7)) << 4) + (size_t)(k & 7) * 2;
       memcpy(dst + off, &b, 2);
     }
@@ -485,6 +501,9 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
     if ((nlf - 1) + (nlh - 1) + 2 > lat2::MASK_LAYERS + 2 || nlf - 1 + nlh - 1 != lat2::MASK_LAYERS)
       return bail(fail(DJ_ERR_UNSUPPORTED, "latent step: %d + %d hidden activations (built for %d)", nlf - 1, nlh - 1, lat2::MASK_LAYERS));
     std::vector<uint8_t> blob[2], blobh[2];  // blobh: forward tiles in IEEE half (DJ_PREC_FP16), backward tiles bf16 as in blob
+    // split-operand program: per entry, how to make the (part 0 = high, 1 = low) tile of (n0, k0), and the layer's scale
+    std::vector<std::function<void(int, int, int, uint8_t*, int)>> gen_x(lat2::MAX_PROG);
+    std::vector<float> scale_x(lat2::MAX_PROG, 1.f);
     int np = 0;
     auto add = [&](int kind, int src, int dst, int n_chunks, int k_stages, int k_steps, int mma_n, int mask_layer, int slot,
                    int bias_off, int after) -> lat2::Layer& {
@@ -531,6 +550,13 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
         lat2::Layer& T = add(kind, buf, head ? 2 : 1 - buf, F.n_chunks, F.k_stages, 8, F.mma_n, head ? 0 : mask, reinj ? 1 : 0,
                              F.bias_off, 0);
         emit(T, [&](int n0, int k0, int rows, uint8_t* dst, bool f16) { pack_tile(W[l], ins[l], outs[l], k_real, n0, k0, rows, dst, f16); });
+        {
+          const float sc = x2_scale(W[l], (size_t)outs[l] * ins[l]);
+          const float* Wl = W[l];
+          const int ldw = ins[l], n_real = outs[l];
+          scale_x[np - 1] = sc;
+          gen_x[np - 1] = [=](int n0, int k0, int rows, uint8_t* dst, int part) { pack_tile_x2(Wl, ldw, n_real, k_real, n0, k0, rows, dst, sc, part); };
+        }
         if (!head) { mask++; buf = 1 - buf; }
       }
     }
@@ -546,6 +572,11 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       {
         lat2::Layer& T = add(lat2::K_BWD, 0, 1, 4, 1, 1, 128, mask0 + nl - 2, 0, 0, 0);
         emit(T, [&](int n0, int, int rows, uint8_t* dst, bool) { pack_tile_head_T(W[nl - 1], ins[nl - 1], n0, rows, dst); });
+        {
+          const float* Wh = W[nl - 1];
+          const int ldw = ins[nl - 1];
+          gen_x[np - 1] = [=](int n0, int, int rows, uint8_t* dst, int) { pack_tile_head_T(Wh, ldw, n0, rows, dst); };
+        }
       }
       buf = 1;
       for (int l = nl - 2; l >= 1; l--) {
@@ -561,10 +592,64 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
         lat2::Layer& T = add(kind, buf, last ? 2 : 1 - buf, n_chunks, k_stages, 8, 128, mask0 + l - 1, slot, 0,
                              (last && net == 1) ? 1 : 0);
         emit(T, [&](int n0, int k0, int rows, uint8_t* dst, bool) { pack_tile_T(W[l], ins[l], out_real, in_real, n0, k0, rows, dst); });
+        {
+          const float* Wl = W[l];
+          const int ldw = ins[l];
+          gen_x[np - 1] = [=](int n0, int k0, int rows, uint8_t* dst, int part) { pack_tile_T_x2(Wl, ldw, out_real, in_real, n0, k0, rows, dst, part); };
+        }
         buf = 1 - buf;
       }
     }
     p->lat_n_prog = np;
+    {  // ---- the split-operand program: same entries, every K = 128 stage as (W_lo, W_hi), stage order as in the forward kernel
+      std::vector<uint8_t> blobx[2];
+      for (int l = 0; l < np; l++) {
+        lat2::Layer& T = p->lat_prog_x[l];
+        T = p->lat_prog[l];
+        T.inv_scale = 1.f;
+        T.k_ranges = T.k_stages;
+        T.korder[0] = T.korder[1] = 0x76543210u;
+        if (T.n_chunks == 0) continue;  // epilogue-only entry
+        const int rows = T.mma_n / 2;
+        if (T.k_steps == 1) {  // K = 16 head-gradient operand: already a compensated product, one stage per chunk
+          for (int j = 0; j < T.n_chunks; j++)
+            for (int r = 0; r < 2; r++) {
+              const size_t o = blobx[r].size();
+              blobx[r].resize(o + T.tile_bytes);
+              gen_x[l](j * T.mma_n + r * rows, 0, rows, blobx[r].data() + o, 0);
+            }
+          continue;
+        }
+        const bool fwd_l = T.kind <= lat2::K_HEAD_H;
+        if (fwd_l) T.inv_scale = 1.f / scale_x[l];
+        const int k_ranges = T.k_ranges;
+        if (2 * k_ranges > 8) return bail(fail(DJ_ERR_UNSUPPORTED, "latent step: more than 4 K ranges per layer"));
+        T.k_stages = (int8_t)(2 * k_ranges);
+        std::vector<std::pair<int, int>> order[2];
+        for (int st = 0; st + 1 < k_ranges; st++) order[0].push_back({1, st});
+        for (int st = 0; st + 1 < k_ranges; st++) order[0].push_back({0, st});
+        order[0].push_back({1, k_ranges - 1});
+        order[0].push_back({0, k_ranges - 1});
+        for (int part = 1; part >= 0; part--)
+          for (int st = 0; st < k_ranges; st++) order[1].push_back({part, st});
+        for (int c = 0; c < 2; c++) {
+          T.korder[c] = 0;
+          for (size_t i = 0; i < order[c].size(); i++) T.korder[c] |= (uint32_t)order[c][i].second << (4 * i);
+        }
+        for (int j = 0; j < T.n_chunks; j++)
+          for (const auto& ps : order[j == 0 ? 0 : 1])
+            for (int r = 0; r < 2; r++)
+              for (int kc = 0; kc < 2; kc++) {
+                const size_t o = blobx[r].size();
+                blobx[r].resize(o + T.tile_bytes);
+                gen_x[l](j * T.mma_n + r * rows, (2 * ps.second + kc) * 64, rows, blobx[r].data() + o, ps.first);
+              }
+      }
+      for (int r = 0; r < 2; r++) {
+        DJ_TRY(cudaMalloc((void**)&p->lat_stream_x[r], blobx[r].size()));
+        DJ_TRY(cudaMemcpy(p->lat_stream_x[r], blobx[r].data(), blobx[r].size(), cudaMemcpyHostToDevice));
+      }
+    }
     for (int r = 0; r < 2; r++) {
       DJ_TRY(cudaMalloc((void**)&p->lat_stream[r], blob[r].size()));
       DJ_TRY(cudaMemcpy(p->lat_stream[r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
@@ -1026,19 +1111,20 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
   simt::fold_kernel<<<dim3((3 * 512 * 32 + 255) / 256, S), 256, 0, st>>>(p->fold, codes_dev, c->tables, C);
   DJ_LAUNCHED();
   DJ_CUDA(cudaMemsetAsync(W.acc, 0, (size_t)S * lat2::ACC_STRIDE * sizeof(float), st));
-  const int64_t tps = (n + lat2::TILE_M - 1) / lat2::TILE_M;
+  const bool x2 = cfg->precision == DJ_PREC_FP16X2;  // split operands, forward and backward (64 samples per CTA)
+  const int tile_pts = x2 ? tc2::TILE_PTS_X2 : lat2::TILE_M;
+  const int64_t tps = (n + tile_pts - 1) / tile_pts;
   const int64_t ntiles = tps * S;
   const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);
-  const int64_t passes = (ntiles + grid - 1) / grid;
-  DJ_CUDA(c->ws_mask.reserve((size_t)passes * grid * lat2::MASK_LAYERS * 8 * 128 * sizeof(unsigned long long)));
+  DJ_CUDA(c->ws_mask.reserve((size_t)grid * lat2::MASK_LAYERS * 8 * 128 * sizeof(unsigned long long)));
   lat2::Params P;
   memset(&P, 0, sizeof P);
-  memcpy(P.prog, p->lat_prog, sizeof(lat2::Layer) * p->lat_n_prog);
+  memcpy(P.prog, x2 ? p->lat_prog_x : p->lat_prog, sizeof(lat2::Layer) * p->lat_n_prog);
   P.n_prog = p->lat_n_prog;
-  const bool half_fwd = cfg->precision == DJ_PREC_FP16 || cfg->precision == DJ_PREC_FP16X2;  // forward in IEEE half (8x finer than bf16: the loss gates follow
-                                                         // the fp32 forward far more often); backward always bf16 (range)
-  P.stream[0] = half_fwd ? p->lat_stream_h[0] : p->lat_stream[0];
-  P.stream[1] = half_fwd ? p->lat_stream_h[1] : p->lat_stream[1];
+  const bool half_fwd = cfg->precision == DJ_PREC_FP16;  // forward in IEEE half (8x finer than bf16: the loss gates follow
+                                                         // the fp32 forward far more often); backward bf16 (range)
+  P.stream[0] = x2 ? p->lat_stream_x[0] : (half_fwd ? p->lat_stream_h[0] : p->lat_stream[0]);
+  P.stream[1] = x2 ? p->lat_stream_x[1] : (half_fwd ? p->lat_stream_h[1] : p->lat_stream[1]);
   P.bias = p->bias_dev;
   P.tables = c->tables;
   P.xyz = W.ptrs; P.sdf = W.ptrs + S; P.nrm = W.ptrs + 2 * S;
@@ -1053,9 +1139,11 @@ static int latent_fwd_bwd_tc(DjPack* p, int S, const float* codes_dev, const int
   if (!p->lat_attr_set) {
     DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
     DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
+    DJ_CUDA(cudaFuncSetAttribute(lat2::latent_tc2_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lat2::SMEM_BYTES));
     p->lat_attr_set = true;
   }
-  if (half_fwd) lat2::latent_tc2_kernel<true><<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
+  if (x2) lat2::latent_tc2_kernel<true, true><<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
+  else if (half_fwd) lat2::latent_tc2_kernel<true><<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
   else lat2::latent_tc2_kernel<false><<<grid, lat2::NTHREADS, lat2::SMEM_BYTES, st>>>(P);
   DJ_LAUNCHED();
   simt::GradFinishParams GP;
@@ -1122,23 +1210,27 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
   const int64_t n = cfg->num_samples;
   const int C = p->L + p->Lb;
   const int log_every = cfg->log_every > 0 ? cfg->log_every : 10;
-  const int64_t log_rows = (cfg->num_iterations + log_every - 1) / log_every;
-  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, cfg->num_iterations, cfg->loss_kind == DJ_LOSS_DEEPSDF ? 1 : 0};
+  const int total = cfg->total_iterations > 0 ? cfg->total_iterations : cfg->num_iterations;
+  const int e0 = cfg->iter_offset;
+  if (e0 < 0 || e0 + cfg->num_iterations > total) return fail(DJ_ERR_INVALID, "dj_latent_optimize: iterations [%d, %d) outside the loop of %d", e0, e0 + cfg->num_iterations, total);
+  const int64_t log_rows = (total + log_every - 1) / log_every;
+  simt::AdamCfg A{cfg->lr, cfg->beta1, cfg->beta2, cfg->eps, total, cfg->loss_kind == DJ_LOSS_DEEPSDF ? 1 : 0};
   if (cfg->precision != DJ_PREC_FP32) {
     // all shapes in one launch per iteration; the kernel gathers every shape's mini-batch rows itself
     LatTcWs T;
     if ((rc = carve_latent_tc(p, n_shapes, T, st))) return rc;
     if ((rc = upload_ptrs(T, n_shapes, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, st))) return rc;
     const int64_t idx_stride = (int64_t)cfg->num_iterations * n;
-    for (int e = 0; e < cfg->num_iterations; e++) {
-      if ((rc = latent_fwd_bwd_tc(p, n_shapes, codes_dev, idx_dev + (size_t)e * n, idx_stride, n, cfg, T, st))) return rc;
+    for (int el = 0; el < cfg->num_iterations; el++) {
+      const int e = e0 + el;
+      if ((rc = latent_fwd_bwd_tc(p, n_shapes, codes_dev, idx_dev + (size_t)el * n, idx_stride, n, cfg, T, st))) return rc;
       float* row = (log_dev && e % log_every == 0) ? log_dev + (size_t)(e / log_every) * 8 : nullptr;
       simt::adam_kernel<<<n_shapes, 256, 0, st>>>(A, e, codes_dev, adam_m_dev, adam_v_dev, T.grad, C, T.terms, row, p->L, C, 256, 8,
                                                   (long long)log_rows * 8);
       DJ_LAUNCHED();
     }
     // a device watchdog that fired during the loop must not go unnoticed (this synchronises the stream once per
-    // optimisation; the caller reads the codes right after anyway)
+    // call; the caller reads the codes right after anyway)
     return check_err_word(p, st);
   }
   // fp32 (reference arithmetic): shape after shape
@@ -1147,8 +1239,9 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
   for (int s = 0; s < n_shapes; s++) {
     float* code = codes_dev + (size_t)s * C;
     const int32_t* idx = idx_dev + (size_t)s * cfg->num_iterations * n;
-    for (int e = 0; e < cfg->num_iterations; e++) {
-      simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev[s], pool_sdf_dev[s], pool_nrm_dev[s], idx + (size_t)e * n, (int)n, W.bx, W.bs, W.bn);
+    for (int el = 0; el < cfg->num_iterations; el++) {
+      const int e = e0 + el;
+      simt::gather_kernel<<<ceil_div(n, 256), 256, 0, st>>>(pool_xyz_dev[s], pool_sdf_dev[s], pool_nrm_dev[s], idx + (size_t)el * n, (int)n, W.bx, W.bs, W.bn);
       DJ_LAUNCHED();
       if ((rc = latent_fwd_bwd(p, code, W.bx, W.bs, W.bn, n, cfg, W, st))) return rc;
       float* row = (log_dev && e % log_every == 0) ? log_dev + ((size_t)s * log_rows + e / log_every) * 8 : nullptr;

@@ -7,12 +7,18 @@ Same arguments, same return value ``(loss_dict, code[1, L+Lb])``, same initialis
 stream (numpy global RNG consumed exactly like core/data.py does), but the 800-iteration loop
 -- batch gather, forward, clamped-L1 + BCE + normal loss, backward to the code only, Adam, lr
 step, loss logging every 10th iteration -- runs on the device without host round trips
-(dj_latent_optimize).  ``sampling_method="device"`` (extension) also draws the schedule on the
-device (dj_sample_schedule), removing the reference's ~60 ms/iteration of host sampling.
+(dj_latent_optimize).  The reference's sampler (62 ms per iteration in numpy) is one native call per block of 100
+iterations on numpy's own MT19937 stream (dj_host_sample_schedule, ~1 ms per iteration, bit-identical rows), drawn on a
+background thread while the device works on the previous block.  ``sampling_method="device"`` (extension) draws
+the schedule on the device instead (dj_sample_schedule; same distribution, not numpy's stream).
 
-Arithmetic follows ``decoder.precision`` (override: ``decoder.latent_precision``): "bf16" runs one fused
-forward + loss + backward tensor-core kernel per iteration (csrc/latent_tc2.cuh; gradient with bf16
-rounding noise, ~1e-2 relative), "fp32" the reference's arithmetic on CUDA cores."""
+Arithmetic follows ``decoder.precision`` (override: ``decoder.latent_precision``):
+  "fp16x2" (default)  split-operand tensor-core step, forward and backward (csrc/latent_tc2.cuh, X2): loss terms within
+                      1e-5 and gradient within 1e-4 of the fp32 / autograd ones -- reproduces the reference's own seeded
+                      run to the tolerance the fp32 path does (tests/test_gpu_latent.py)
+  "fp32"              the reference's arithmetic on CUDA cores (13x slower)
+  "bf16" / "fp16"     single-pass tensor-core step, 3.8x faster than fp16x2; gradient with ~1e-2 / 3e-3 relative
+                      rounding noise, loss gates decided on a 16-bit forward: opt-in throughput modes"""
 import os
 from collections import defaultdict
 
@@ -84,25 +90,76 @@ def init_code(latent_size, break_latent_size, stat):
 
 
 def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, lambda1, lambda3, clamp_dist,
-                  l2reg=True, code_reg_lambda=1e-4, log_every=10, precision="fp32", loss_kind=0):
+                  l2reg=True, code_reg_lambda=1e-4, log_every=10, precision="fp32", loss_kind=0, schedule_blocks=None,
+                  total_iterations=None):
     """Device loop.  pool_* CUDA f32 tensors ([M,3], [M], [M,3]); schedule CUDA int32
-    [iterations, num_samples].  Returns (log [ceil(it/log_every), 8] CUDA, code [1, L+Lb] CUDA)."""
+    [iterations, num_samples].  Returns (log [ceil(it/log_every), 8] CUDA, code [1, L+Lb] CUDA).
+
+    ``schedule_blocks`` (instead of ``schedule``): an iterator of host int32 arrays [n_k, num_samples] whose lengths sum
+    to ``total_iterations`` -- the loop runs block by block (DjLatentCfg.iter_offset), each block uploaded and enqueued
+    as soon as it arrives, so that a host sampler producing the schedule overlaps with the device work."""
     dev = pool_xyz.device
     pack = decoder.pack(dev)
-    iters, ns = int(schedule.shape[0]), int(schedule.shape[1])
-    cfg = _lib.LatentCfg(iters, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
-                         float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, int(log_every),
-                         _lib.PREC[precision], int(loss_kind))
+    if schedule_blocks is None:
+        schedule_blocks = [schedule]
+        total_iterations = int(schedule.shape[0])
+    total = int(total_iterations)
     code = code0.detach().reshape(-1).to(device=dev, dtype=torch.float32).clone().contiguous()
     m = torch.zeros_like(code)
     v = torch.zeros_like(code)
-    log = torch.zeros(((iters + log_every - 1) // log_every, 8), device=dev, dtype=torch.float32)
-    with torch.cuda.device(dev):
-        _lib.check(_lib.lib().dj_latent_optimize(
-            pack.handle, code.data_ptr(), m.data_ptr(), v.data_ptr(), pool_xyz.data_ptr(), pool_sdf.data_ptr(),
-            pool_nrm.data_ptr(), pool_xyz.shape[0], schedule.data_ptr(), _lib.ctypes.byref(cfg), log.data_ptr(),
-            _lib.stream_ptr()))
+    log = torch.zeros(((total + log_every - 1) // log_every, 8), device=dev, dtype=torch.float32)
+    done, keep = 0, []
+    for block in schedule_blocks:
+        if not isinstance(block, torch.Tensor):
+            block = torch.from_numpy(np.ascontiguousarray(block, dtype=np.int32))
+        block = block.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        keep.append(block)  # the enqueued iterations read it
+        n_k, ns = int(block.shape[0]), int(block.shape[1])
+        cfg = _lib.LatentCfg(n_k, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
+                             float(code_reg_lambda), int(bool(l2reg)), 0.9, 0.999, 1e-8, int(log_every),
+                             _lib.PREC[precision], int(loss_kind), done, total)
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().dj_latent_optimize(
+                pack.handle, code.data_ptr(), m.data_ptr(), v.data_ptr(), pool_xyz.data_ptr(), pool_sdf.data_ptr(),
+                pool_nrm.data_ptr(), pool_xyz.shape[0], block.data_ptr(), _lib.ctypes.byref(cfg), log.data_ptr(),
+                _lib.stream_ptr()))
+        done += n_k
+    if done != total:
+        raise ValueError("schedule blocks cover %d of %d iterations" % (done, total))
+    if len(keep) > 1:
+        torch.cuda.current_stream(dev).synchronize()
     return log, code.reshape(1, -1)
+
+
+def _schedule_blocks(b_sdf_gt, num_iterations, num_samples, uniform_ratio, block=100):
+    """make_schedule in blocks of `block` iterations on a background thread (numpy's global stream, in order): the
+    native sampler releases the GIL, the consumer enqueues block k on the device while block k + 1 is drawn."""
+    import queue
+    import threading
+    q = queue.Queue(maxsize=4)
+
+    def produce():
+        try:
+            e = 0
+            while e < num_iterations:
+                n_k = min(block, num_iterations - e)
+                q.put(make_schedule(b_sdf_gt, n_k, num_samples, uniform_ratio))
+                e += n_k
+            q.put(None)
+        except BaseException as exc:  # noqa: BLE001 -- re-raised in the consumer (NoSamplesError keeps its type)
+            q.put(exc)
+
+    t = threading.Thread(target=produce, daemon=True)
+    t.start()
+    while True:
+        item = q.get()
+        if item is None:
+            break
+        if isinstance(item, BaseException):
+            t.join()
+            raise item
+        yield item
+    t.join()
 
 
 def optimize_codes(decoder, codes0, pools, schedules, lr, lambda1, lambda3, clamp_dist, l2reg=True, code_reg_lambda=1e-4,
@@ -193,11 +250,18 @@ def reconstruct(decoder, num_iterations, latent_size, break_latent_size, test_sd
             _lib.check(_lib.lib().dj_sample_schedule(pool_sdf.data_ptr(), pool_sdf.shape[0], int(num_iterations),
                                                      int(num_samples), 0.2, seed, sched.data_ptr(), _lib.stream_ptr()))
     else:
-        sched = torch.from_numpy(make_schedule(b_sdf_gt, num_iterations, num_samples, 0.2)).to(dev)
+        sched = None  # the reference's sampler, drawn block by block while the device runs (same stream, same rows)
 
-    log, code = optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, sched, lr, lambda1, lambda3, clamp_dist,
-                              l2reg=l2reg, code_reg_lambda=code_reg_lambda, log_every=10,
-                              precision=getattr(decoder, "latent_precision", None) or getattr(decoder, "precision", "bf16"))
+    prec = getattr(decoder, "latent_precision", None) or getattr(decoder, "precision", "fp16x2")
+    if sched is None:
+        vals = np.ascontiguousarray(_data._f32(np.asarray(b_sdf_gt).reshape(-1)), dtype=np.float32)
+        log, code = optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, None, lr, lambda1, lambda3, clamp_dist,
+                                  l2reg=l2reg, code_reg_lambda=code_reg_lambda, log_every=10, precision=prec,
+                                  schedule_blocks=_schedule_blocks(vals, num_iterations, num_samples, 0.2),
+                                  total_iterations=num_iterations)
+    else:
+        log, code = optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, sched, lr, lambda1, lambda3, clamp_dist,
+                                  l2reg=l2reg, code_reg_lambda=code_reg_lambda, log_every=10, precision=prec)
     log = log.cpu().numpy()
     loss_dict = defaultdict(lambda: [])
     for row in log:

@@ -131,6 +131,13 @@ typedef struct DjLatentCfg {
   int32_t log_every;        /* 10 (:203)                                             */
   int32_t precision;
   int32_t loss_kind;        /* DJ_LOSS_DEEPJOIN (0) | DJ_LOSS_DEEPSDF (1)            */
+  /* continuation of a loop in pieces (the host sampler of the reference-exact path produces the schedule block by
+   * block while the device works on the previous block): this call runs iterations iter_offset ..
+   * iter_offset + num_iterations - 1 of a loop of total_iterations (0 = num_iterations) -- lr step, Adam bias
+   * correction and log rows follow the GLOBAL iteration; adam_m / adam_v / codes / log carry over between calls,
+   * idx_dev holds this call's num_iterations rows only */
+  int32_t iter_offset;
+  int32_t total_iterations;
 } DjLatentCfg;
 /* DJ_LOSS_DEEPSDF: the baseline's objective (reconstruct_deepsdf.py:109-134) on the single-net pack a
  * DeepSDF decoder builds: mean |clamp(tanh(y0), +-d) - clamp(sdf, +-d)| + reg; lambda1 / lambda3 and the
