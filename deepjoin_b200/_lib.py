@@ -8,7 +8,8 @@ import numpy as np
 from .core import errors
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libdeepjoin_b200.so")
+# DEEPJOIN_B200_LIB: load another build of the same ABI (the -DDJ_DEBUG diagnostics library of tools/)
+LIB_PATH = os.environ.get("DEEPJOIN_B200_LIB") or os.path.join(_HERE, "lib", "libdeepjoin_b200.so")
 
 (OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SURFACE, ERR_LEVEL_RANGE, ERR_NO_SAMPLES, ERR_BAD_NET, ERR_DEVICE,
  ERR_PERMISSION, ERR_IO) = range(11)
@@ -62,10 +63,14 @@ SIGNATURES = {
     "dj_create_mesh_fetch64": (c_i, [c_p, c_p, c_p, c_p]),
     "dj_mesh_merge_vertices": (c_i, [c_p, c_p, c_i64, c_p, c_i64, ctypes.POINTER(c_i64), c_p]),
     "dj_nn_query": (c_i, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p]),
-    "dj_debug_umma_probe": (c_i, [c_p, c_p, c_i, c_i, c_i, ctypes.c_uint32, ctypes.c_uint64, c_p]),
-    "dj_debug_read_prof": (c_i, [c_p, c_p, c_i]),
     "dj_launch_count": (c_i64, [c_i]),
     "dj_host_sample_schedule": (c_i, [c_p, c_p, c_p, c_i64, ctypes.c_double, c_i, c_i, c_i, c_p]),
+}
+
+# diagnostics that only a -DDJ_DEBUG build exports (python -m deepjoin_b200.build --debug; DEEPJOIN_B200_LIB selects it)
+DEBUG_SIGNATURES = {
+    "dj_debug_umma_probe": (c_i, [c_p, c_p, c_i, c_i, c_i, ctypes.c_uint32, ctypes.c_uint64, c_p]),
+    "dj_debug_read_prof": (c_i, [c_p, c_p, c_i]),
 }
 
 _lib = None
@@ -83,6 +88,11 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        for name, (res, args) in DEBUG_SIGNATURES.items():
+            if hasattr(L, name):
+                fn = getattr(L, name)
+                fn.restype = res
+                fn.argtypes = args
         got = L.dj_abi_version()
         if got != ABI_VERSION:
             raise RuntimeError("deepjoin_b200: ABI version mismatch: library %d, bindings %d (rebuild: python -m deepjoin_b200.build --force)" % (got, ABI_VERSION))

@@ -18,7 +18,9 @@
 #include "sampler.cuh"
 #include "mesh_merge.cuh"
 #include "nn.cuh"
+#ifdef DJ_DEBUG
 #include "debug_probe.cuh"
+#endif
 
 using namespace dj;
 
@@ -761,7 +763,9 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
         for (int r = 0; r < 2; r++) P.nets[net].stream[r] = p->stream2h[net][r];
     P.net_mask = net_mask;
     P.grid_mode = G.on;
+#ifdef DJ_DEBUG
     if (const char* e = getenv("DEEPJOIN_B200_DEBUG")) P.debug = atoi(e);
+#endif
     P.bias = p->bias_dev;
     P.tables = cx->tables;
     P.xyz = xyz_dev;
@@ -778,14 +782,18 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     const int grid = (int)std::min<int64_t>((ntiles + 1) / 2 * 2, p->num_sms / 2 * 2);  // whole CTA pairs
     if (!p->tc_attr_set2) {
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+#ifdef DJ_DEBUG
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+#endif
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       p->tc_attr_set2 = true;
     }
     if (x2) tc2::tc2_forward_kernel<0, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+#ifdef DJ_DEBUG
     else if (P.debug) tc2::tc2_forward_kernel<1, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+#endif
     else tc2::tc2_forward_kernel<0, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     DJ_LAUNCHED();
     return DJ_OK;
@@ -1623,6 +1631,7 @@ extern "C" int dj_nn_query(const float* queries_dev, int64_t n, const float* tar
   return DJ_OK;
 }
 
+#ifdef DJ_DEBUG
 // ====================================================================== debug probe (not product path)
 // A_host [128,K], W_host [128,K] fp32 (nn.Linear layout); D_host [128,128] = bf16(A) . bf16(W)^T.
 // desc_tmpl == 0 / k_adv_bytes == 0 / idesc == 0 select the encodings the product kernel uses.
@@ -1669,3 +1678,4 @@ extern "C" int dj_debug_umma_probe(const float* A_host, const float* W_host, int
   if (h) return fail(DJ_ERR_DEVICE, "umma probe watchdog 0x%08x", h);
   return DJ_OK;
 }
+#endif  // DJ_DEBUG

@@ -251,6 +251,9 @@ int dj_mesh_merge_vertices(DjMcWork* work, double* verts_dev, int64_t n_verts, i
 int dj_nn_query(const float* queries_dev, int64_t n, const float* targets_dev, int64_t m, float* dist2_dev,
                 int32_t* idx_dev, void* stream);
 
+#ifdef DJ_DEBUG
+/* The two entry points below exist only in a library built with -DDJ_DEBUG (python -m deepjoin_b200.build --debug,
+ * which writes lib/libdeepjoin_b200_debug.so): diagnostics for tools/, not part of the product library. */
 /* DEBUG ONLY (tools/gpu_diag.py): one 128x128xK bf16 UMMA built from the product kernel's pieces;
  * D_host [128,128] = bf16(A_host [128,K]) . bf16(W_host [128,K])^T.  Zero for k_adv_bytes / idesc /
  * desc_tmpl selects the product encodings. */
@@ -260,6 +263,7 @@ int dj_debug_umma_probe(const float* A_host, const float* W_host, int K, int use
 /* DEBUG ONLY: per-CTA cycle counters of the last tensor-core forward launched with
  * DEEPJOIN_B200_DEBUG & 8 ([CTA][16] words; layout in csrc/mlp_tc2.cuh). */
 int dj_debug_read_prof(DjPack* pack, unsigned long long* out_host, int n_words);
+#endif /* DJ_DEBUG */
 
 /* counters for bench.py: kernels launched by this library since the last reset */
 int64_t dj_launch_count(int reset);

@@ -194,6 +194,32 @@ def test_split_operand_latent_gradient_vs_autograd(kind, n):
     assert np.allclose(terms.cpu().numpy(), np.asarray(t), rtol=0, atol=5e-5)
 
 
+@pytest.mark.parametrize("precision", ["fp32", "fp16x2"])
+def test_occupancy_target_of_the_fused_loss(precision):
+    """tensor_sdf_to_occ inside the fused loss (a8; reconstruct.py:169 -> core/reconstruct.py:33-34): a target of exactly
+    0 or -0 counts as inside.  The BCE term alone (lambda1 = lambda3 = 0) against the oracle on a batch made of such rows."""
+    from deepjoin_b200 import reconstruct as R
+    dec = util.make_decoder(0, "trained_norm", precision=precision)
+    net = util.oracle_net(0, "trained_norm", "float64")
+    xyz, sdf, nrm = synth.make_sample_set(4000, seed=1)
+    x, m = (torch.from_numpy(a[:512].astype(np.float32)) for a in (xyz, nrm))
+    s = torch.from_numpy(sdf[:512].astype(np.float32)).clone()
+    s[0:100] = 0.0
+    s[100:200] = -0.0
+    s[200:300] = 1e-30
+    s[300:400] = -1e-30
+    code = util.trained_code(0)
+    kw = dict(lambda1=0.0, lambda3=0.0, l2reg=False)
+    ref, t = O.latent_grad(net, code.double(), x.double(), s.double(), m.double(), **kw)
+    grad, terms = R.latent_grad(dec, code.cuda(), x.cuda(), s.cuda(), m.cuda(), precision=precision, **kw)
+    assert abs(float(terms[2]) - t[2]) < 5e-5 and abs(float(terms[0]) - t[2]) < 5e-5 and float(terms[1]) == 0.0
+    assert float((grad.cpu().double() - ref).abs().max()) <= 3e-3 * float(ref.abs().max()) + 1e-7
+    flipped = s.clone()
+    flipped[0:200] = 1e-30  # the same rows counted as outside give a different loss: the target matters
+    _, t2 = O.latent_grad(net, code.double(), x.double(), flipped.double(), m.double(), **kw)
+    assert abs(t2[2] - t[2]) > 1e-3
+
+
 def test_split_operand_latent_options():
     from deepjoin_b200 import reconstruct as R
     dec = util.make_decoder(1, "trained_norm", precision="fp16x2")

@@ -21,11 +21,16 @@ def test_library_exports_every_declared_symbol():
     build.build()
     header = open(os.path.join(ROOT, "include", "deepjoin_b200.h")).read()
     header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    debug_block = re.search(r"#ifdef DJ_DEBUG(.*?)#endif", header, flags=re.S).group(1)
+    assert set(re.findall(r"\b(dj_[a-z0-9_]+)\s*\(", debug_block)) == set(_lib.DEBUG_SIGNATURES)
+    header = header.replace(debug_block, "")  # diagnostics are not part of the product library
     declared = set(re.findall(r"\b(dj_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     L = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(L, name), name
+    for name in _lib.DEBUG_SIGNATURES:
+        assert not hasattr(L, name), name
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     # one ABI number everywhere: header #define, ctypes bindings, built library (and __graft_entry__.build(), below)
     abi = int(re.search(r"#define\s+DJ_ABI_VERSION\s+(\d+)", header).group(1))
@@ -55,6 +60,21 @@ def test_status_codes_map_to_reference_exceptions():
     with pytest.raises(RuntimeError):
         _lib.check(_lib.ERR_BAD_NET)
     assert issubclass(errors.IsosurfaceExtractionError, RuntimeError)
+
+
+def test_tensor_sdf_helpers_known_answers():
+    """core/reconstruct.py:33-42 (a8): occ = 1 where sdf <= 0 (zero counts as inside), udf = |sdf|, and the way back."""
+    from deepjoin_b200.core import reconstruct as R
+    sdf = torch.tensor([[-2.0], [-1e-30], [-0.0], [0.0], [1e-30], [3.5], [float("inf")], [-float("inf")]])
+    occ = R.tensor_sdf_to_occ(sdf)
+    assert occ.dtype == sdf.dtype and occ.reshape(-1).tolist() == [1.0, 1.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0]
+    fin = sdf[:6]
+    udf = R.tensor_sdf_to_udf(fin)
+    assert torch.equal(udf.reshape(-1), torch.tensor([2.0, 1e-30, 0.0, 0.0, 1e-30, 3.5]))
+    back = R.tensor_udf_to_sdf(udf, R.tensor_sdf_to_occ(fin))
+    assert torch.equal(back.abs(), fin.abs()) and torch.equal(back[[0, 1, 4, 5]], fin[[0, 1, 4, 5]])
+    soft = R.tensor_udf_to_sdf(torch.tensor([1.0, 1.0, 1.0]), torch.tensor([0.49, 0.51, 1.0]))  # occ is rounded first
+    assert soft.tolist() == [1.0, -1.0, -1.0]
 
 
 def test_null_arguments_are_rejected_without_a_gpu():

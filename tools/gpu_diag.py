@@ -12,7 +12,9 @@ OUT = os.path.join(ROOT, "gpurun_out")
 
 
 def bf16_round(a):
-    import numpy as np
+    # the dj_debug_* entry points live in the diagnostics build only (python -m deepjoin_b200.build --debug)
+os.environ.setdefault("DEEPJOIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deepjoin_b200", "lib", "libdeepjoin_b200_debug.so"))
+import numpy as np
     u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
     u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
     return u.astype(np.uint32).view(np.float32)

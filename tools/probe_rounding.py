@@ -1,6 +1,8 @@
 """How does tcgen05.mma accumulate in fp32?  bf16-exact operands (exact products), compare with the fp64 sum."""
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+# the dj_debug_* entry points live in the diagnostics build only (python -m deepjoin_b200.build --debug)
+os.environ.setdefault("DEEPJOIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deepjoin_b200", "lib", "libdeepjoin_b200_debug.so"))
 import numpy as np
 import torch
 from deepjoin_b200 import _lib
