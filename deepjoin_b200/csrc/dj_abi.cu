@@ -1327,7 +1327,10 @@ extern "C" int dj_sample_schedule(const float* pool_sdf_dev, int64_t pool_n, int
 struct DjMcWork {
   int device = 0;
   mc::Dims D{};
-  DevBuf var, counts, offs, edge, misc, verts, faces, merge, wide, volbuf;
+  DevBuf records, counts, offs, edge, misc, verts, faces, merge, wide, volbuf;
+  int64_t n_rec = 0;        // cut cells of the last dj_mc_count
+  int arena_cap = 0;        // records per arena of the record list (mc::NARENA arenas)
+  int span = 32;            // the fullest arena of the last count, rounded up to 32: what the emit kernels walk
   // host-facing create_mesh entry points (dj_create_mesh_count / fetch): this workspace's own stream, so that two
   // host threads meshing with one DjPack (each with its own DjMcWork) neither share per-shape tables nor order
   // against each other
@@ -1361,7 +1364,7 @@ extern "C" int dj_mc_create(int device, DjMcWork** out) {
 extern "C" int dj_mc_destroy(DjMcWork* w) {
   if (!w) return DJ_OK;
   DeviceGuard g(w->device);
-  for (DevBuf* b : {&w->var, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge, &w->wide, &w->volbuf}) b->release();
+  for (DevBuf* b : {&w->records, &w->counts, &w->offs, &w->edge, &w->misc, &w->verts, &w->faces, &w->merge, &w->wide, &w->volbuf}) b->release();
   if (w->own_stream) cudaStreamDestroy(w->own_stream);
   delete w;
   return DJ_OK;
@@ -1379,39 +1382,67 @@ extern "C" int dj_mc_count(DjMcWork* w, const float* vol_dev, int n0, int n1, in
   D.c1 = n1 - 1; D.c2 = n2 - 1;
   D.ncells = (int64_t)(n0 - 1) * D.c1 * D.c2;
   D.level = level;
-  w->vol = vol_dev;
-  if (n0 - 1 > 65535) return fail(DJ_ERR_UNSUPPORTED, "dj_mc_count: more than 65535 cell layers");
-  w->bpp = (int)(((int64_t)D.c1 * D.c2 + mc::CB - 1) / mc::CB);
-  w->nblocks = (int64_t)(n0 - 1) * w->bpp;
-  const int64_t nsamp = (int64_t)n0 * n1 * n2;
-  DJ_CUDA(w->var.reserve((size_t)D.ncells * sizeof(uint16_t)));
-  DJ_CUDA(w->counts.reserve((size_t)w->nblocks * sizeof(int2)));
-  DJ_CUDA(w->offs.reserve((size_t)w->nblocks * sizeof(int2)));
-  const int64_t ngroups = (w->nblocks + mc::SG - 1) / mc::SG;
-  DJ_CUDA(w->misc.reserve(64 + (size_t)ngroups * sizeof(longlong2)));
-  long long* totals = w->misc.as<long long>();
-  int* mm = reinterpret_cast<int*>(totals + 2);
-  longlong2* group_off = reinterpret_cast<longlong2*>(totals + 8);
-  if (check_range) {
-    const int init[2] = {0x7FFFFFFF, (int)0x80000000};
-    DJ_CUDA(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st));
-    mc::minmax_kernel<<<1184, 256, 0, st>>>(vol_dev, nsamp, mm);
-    DJ_LAUNCHED();
+  {  // largest float32 <= level (classification compares float32 samples in float32, exactly as the double test would)
+    float lf = (float)level;
+    if ((double)lf > level) lf = nextafterf(lf, -INFINITY);
+    if (lf == 0.f) lf = 0.f;  // +0: the kernel reads the sign bit of (level_lo - v)
+    D.level_lo = lf;
   }
-  const dim3 mc_grid((unsigned)w->bpp, (unsigned)(n0 - 1));
-  DJ_CUDA(cudaMemsetAsync(w->counts.as<int2>(), 0, (size_t)w->nblocks * sizeof(int2), st));
-  mc::classify_kernel<<<mc_grid, mc::CB, 0, st>>>(D, vol_dev, w->var.as<uint16_t>(), w->counts.as<int2>());
-  DJ_LAUNCHED();
-  mc::scan_groups_kernel<<<(unsigned)ngroups, mc::SG, 0, st>>>(w->counts.as<int2>(), w->nblocks, w->offs.as<int2>(), group_off);
-  DJ_LAUNCHED();
-  mc::scan_totals_kernel<<<1, mc::SG, 0, st>>>(group_off, ngroups, totals);
-  DJ_LAUNCHED();
+  w->vol = vol_dev;
+  if (n0 - 1 > 65535 || (n1 - 1 + mc::ROWS - 1) / mc::ROWS > 65535) return fail(DJ_ERR_UNSUPPORTED, "dj_mc_count: more than 65535 cell layers / row groups");
+  if (D.ncells >= 0x7FFFFFFFLL) return fail(DJ_ERR_UNSUPPORTED, "dj_mc_count: more than 2^31 - 1 cells in one slab");
+  D.wpr = (D.c2 + mc::UC - 1) / mc::UC;
+  const int bpr = (D.wpr + mc::CB / 32 - 1) / (mc::CB / 32);                 // blocks along x
+  w->bpp = ((D.c1 + mc::ROWS - 1) / mc::ROWS) * bpr;                         // blocks per cell layer
+  w->nblocks = (int64_t)(n0 - 1) * D.c1 * D.wpr;                             // scan units: 31-cell chunks in sweep order
+  if (w->nblocks >= 0x7FFFFFFFLL) return fail(DJ_ERR_UNSUPPORTED, "dj_mc_count: too many scan units");
+  DJ_CUDA(w->counts.reserve((size_t)w->nblocks * sizeof(uint2)));
+  DJ_CUDA(w->offs.reserve((size_t)w->nblocks * sizeof(int2)));
+  uint2* units = w->counts.as<uint2>();
+  const int64_t ngroups = (w->nblocks + mc::SG - 1) / mc::SG;
+  DJ_CUDA(w->misc.reserve(64 + mc::NARENA * sizeof(int) + (size_t)ngroups * sizeof(longlong2)));
+  long long* totals = w->misc.as<long long>();     // [0] vertices [1] triangles [2] (min, max) ordered ints
+  int* mm = reinterpret_cast<int*>(totals + 2);
+  int* cursors = reinterpret_cast<int*>(totals + 8);  // [NARENA] records per arena
+  longlong2* group_off = reinterpret_cast<longlong2*>(cursors + mc::NARENA);
+  const dim3 mc_grid((unsigned)bpr, (unsigned)((D.c1 + mc::ROWS - 1) / mc::ROWS), (unsigned)(n0 - 1));
+  // The record list (one entry per cut cell, ~3 % of the cells): NARENA arenas of arena_cap entries.  It starts at
+  // 1/16 of the cells and grows on demand: the kernel counts past the capacity, the sweep is then repeated once
+  // with arenas that fit (the workspace keeps the larger size).
+  w->arena_cap = (int)std::max<int64_t>(std::max(w->arena_cap, 64), D.ncells / 16 / mc::NARENA);
   long long h[3];
-  DJ_CUDA(cudaMemcpyAsync(h, totals, sizeof h, cudaMemcpyDeviceToHost, st));
-  DJ_CUDA(cudaStreamSynchronize(st));
-  if (check_range) {
+  std::vector<int> hc(mc::NARENA);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    DJ_CUDA(w->records.reserve((size_t)w->arena_cap * mc::NARENA * sizeof(mc::Record)));
+    DJ_CUDA(cudaMemsetAsync(cursors, 0, mc::NARENA * sizeof(int), st));
+    DJ_CUDA(cudaMemsetAsync(units, 0, (size_t)w->nblocks * sizeof(uint2), st));  // only units with cut cells are written
+    mc::classify_kernel<<<mc_grid, mc::CB, 0, st>>>(D, vol_dev, units, w->records.as<mc::Record>(), w->arena_cap, cursors);
+    DJ_LAUNCHED();
+    mc::scan_groups_kernel<<<(unsigned)ngroups, mc::SG, 0, st>>>(units, w->nblocks, w->offs.as<int2>(), group_off);
+    DJ_LAUNCHED();
+    mc::scan_totals_kernel<<<1, mc::SG, 0, st>>>(group_off, ngroups, totals);
+    DJ_LAUNCHED();
+    DJ_CUDA(cudaMemcpyAsync(h, totals, sizeof h, cudaMemcpyDeviceToHost, st));
+    DJ_CUDA(cudaMemcpyAsync(hc.data(), cursors, mc::NARENA * sizeof(int), cudaMemcpyDeviceToHost, st));
+    DJ_CUDA(cudaStreamSynchronize(st));
+    int most = 0;
+    w->n_rec = 0;
+    for (int a = 0; a < mc::NARENA; a++) { most = std::max(most, hc[a]); w->n_rec += hc[a]; }
+    w->span = std::max(32, (most + 31) / 32 * 32);
+    if (most <= w->arena_cap) break;
+    if (attempt == 1) return fail(DJ_ERR_DEVICE, "dj_mc_count: record arena overflow after growing (%d > %d)", most, w->arena_cap);
+    w->arena_cap = most + most / 4 + 64;
+  }
+  if (check_range && h[1] == 0) {
+    // skimage's ValueError: level outside [min, max].  A cut cell has samples on both sides of the level, so the range
+    // only has to be looked at when nothing was cut (then this pass over the volume decides which error it is)
+    const int init[2] = {0x7FFFFFFF, (int)0x80000000};  // min, max (ordered ints)
+    DJ_CUDA(cudaMemcpyAsync(mm, init, sizeof init, cudaMemcpyHostToDevice, st));
+    mc::minmax_kernel<<<1184, 256, 0, st>>>(vol_dev, (int64_t)n0 * n1 * n2, mm);
+    DJ_LAUNCHED();
     int hm[2];
-    memcpy(hm, &h[2], sizeof hm);
+    DJ_CUDA(cudaMemcpyAsync(hm, mm, sizeof hm, cudaMemcpyDeviceToHost, st));
+    DJ_CUDA(cudaStreamSynchronize(st));
     auto unord = [](int i) { int b = i >= 0 ? i : i ^ 0x7FFFFFFF; float f; memcpy(&f, &b, 4); return f; };
     const float lo = unord(hm[0]), hi = unord(hm[1]);
     if (level < (double)lo || level > (double)hi)
@@ -1440,12 +1471,17 @@ extern "C" int dj_mc_fill(DjMcWork* w, int descent, float* verts_dev, int32_t* f
     mc::seam_fill_kernel<<<ceil_div(np * 2, 256), 256, 0, st>>>(w->edge.as<int>(), np);
     DJ_LAUNCHED();
   }
-  const dim3 mc_grid((unsigned)w->bpp, (unsigned)(D.n0 - 1));
-  const longlong2* group_off = reinterpret_cast<const longlong2*>(w->misc.as<long long>() + 8);
-  mc::emit_vertices_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->vol, w->var.as<uint16_t>(), w->counts.as<int2>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), verts_dev);
-  DJ_LAUNCHED();
-  mc::emit_faces_kernel<<<mc_grid, mc::CB, 0, st>>>(D, w->var.as<uint16_t>(), w->counts.as<int2>(), w->offs.as<int2>(), group_off, w->edge.as<int>(), descent, faces_dev);
-  DJ_LAUNCHED();
+  const int* cursors = reinterpret_cast<const int*>(w->misc.as<long long>() + 8);
+  const longlong2* group_off = reinterpret_cast<const longlong2*>(cursors + mc::NARENA);
+  if (w->n_rec > 0) {
+    const unsigned grid = (unsigned)(((int64_t)w->span * mc::NARENA + mc::EB - 1) / mc::EB);
+    mc::emit_vertices_kernel<<<grid, mc::EB, 0, st>>>(D, w->records.as<mc::Record>(), w->span, w->arena_cap, cursors, w->offs.as<int2>(), group_off,
+                                                     w->edge.as<int>(), verts_dev);
+    DJ_LAUNCHED();
+    mc::emit_faces_kernel<<<grid, mc::EB, 0, st>>>(D, w->records.as<mc::Record>(), w->span, w->arena_cap, cursors, w->offs.as<int2>(), group_off,
+                                                  w->edge.as<int>(), descent, faces_dev);
+    DJ_LAUNCHED();
+  }
   return DJ_OK;
 }
 

@@ -8,14 +8,24 @@
 //   * vertex id = exclusive scan over cells (sweep order) of owned-vertex counts + rank of the
 //     edge among the cell's owned edges in first-appearance order of its triangle list;
 //   * face offset = exclusive scan of triangle counts.
-// Kernels: classify (cube index + asymptotic-decider variant, per-block counts, warp-shuffle
-// reduction) -> two-level scan of the block counts -> emit vertices (+ edge->id table) -> emit faces.
-// A block owns 256 consecutive cells of one cell layer (blockIdx.y = layer, so the sweep-order block
-// index needs no 64-bit division).  Only ~3 % of the cells are cut by the surface: the emit kernels
-// compact the block's owned vertices / triangles into shared memory with the block scan and then give
-// every thread ONE vertex (one inverse-distance interpolation in float64) or ONE triangle, instead of
-// one cell with up to 13 vertices.  HBM-bound: 4 B/sample read by classify; the emit passes stream the
-// 2 B/cell variant array.
+// Kernels (round 2): the volume is read ONCE.
+//   classify_kernel   the unit of work and of the scan is a warp's 31 consecutive cells of one row (x fastest; lane 31
+//                     only carries the samples at x + 1 of lane 30's cell); warps never synchronise with each other.
+//                     A lane loads its samples at x and takes what it needs of x + 1 from its neighbour (one shuffle
+//                     of the packed "above the level" flags); a warp pass covers 4 rows (10 coalesced reads in flight).
+//                     ~97 % of the cells are not cut: they cost 8 compares and nothing is stored for them.  A cut
+//                     cell gets a RECORD (cell, variant, its exclusive (vertex, triangle) prefix inside the unit,
+//                     the 8 corner values) in a record list; the unit reserves its run with one atomic on one of
+//                     NARENA cursors (unit index mod NARENA: a single cursor would serialise ~100,000 returning
+//                     atomics on one L2 address).  Per live unit: counts.
+//   scan_*            two-level exclusive scan of the per-unit (vertex, triangle) counts in sweep order; totals for
+//                     the host.  (The volume's min / max -- skimage's level-range check -- is only computed when no
+//                     cell is cut: a cut cell proves the level is inside the range.)
+//   emit_vertices /   dense over the records, in the order they were stored (NOT sweep order: a record carries its
+//   emit_faces        block and prefix, so its global ids are block offset + prefix whatever the storage order):
+//                     one thread per cut cell, 1.5 owned vertices / 2.8 triangles on average.
+// HBM-bound: 4 B/sample read once + 12 B per vertex + 12 B per face written; the edge -> id table (4 int per sample,
+// touched only at intersected edges) is the only scattered traffic.
 #pragma once
 #include "common.cuh"
 
@@ -25,9 +35,18 @@
 namespace dj {
 namespace mc {
 
-constexpr int CB = 256;  // cells per block
+constexpr int CB = 256;  // cells per block (consecutive in x, one row)
 // variants of the two configurations without a surface (DJ_MC_VARBASE[0], DJ_MC_VARBASE[255]; no ambiguous faces)
 constexpr int DJ_MC_VAR_EMPTY0 = 0, DJ_MC_VAR_EMPTY255 = 655;
+// one cut cell: what the emit kernels need, so that they never touch the volume
+struct __align__(16) Record {
+  int cell;     // (zr * c1 + y) * c2 + x within the slab
+  int unit;     // sweep-order index of the cell's 32-cell unit (its scanned offsets are the base of the ids)
+  int var;      // case-table variant
+  int pre;      // exclusive prefix inside the unit: owned vertices | triangles << 16
+  float f[8];   // corner values (float32 as stored in the volume)
+};
+constexpr int NARENA = 1024;  // the record list is NARENA regions of arena_cap records, one cursor each
 // edges that are owned only on the x==0 / y==0 / z==0 boundary of the slab
 constexpr unsigned MX = 0x988, MY = 0x311, MZ = 0x00F;
 constexpr double FLT_EPS_D = 1.1920928955078125e-07;
@@ -37,47 +56,26 @@ struct Dims {
   int z_off;        // global index of the slab's first plane (added to axis-0 coordinates)
   int seam;         // 1: upper slab of a sharded sweep -- plane-0 edges belong to the slab below
   int c1, c2;       // cells along axis 1 / 2
+  int wpr;          // units (UC = 31 cells) per row: ceil(c2 / 31)
   int64_t ncells;
   double level;
+  float level_lo;   // the largest float32 <= level: for a float32 sample v, ((double)v - level > 0) == (v > level_lo) exactly
 };
 
-// block -> cells: blockIdx.y = cell layer zr, blockIdx.x*CB + threadIdx.x = cell within the layer (row-major y, x)
-__device__ __forceinline__ bool block_cell(const Dims& D, int t, int& zr, int& y, int& x, int64_t& ci) {
-  zr = (int)blockIdx.y;
-  const unsigned idx = blockIdx.x * (unsigned)CB + (unsigned)t;
-  const unsigned plane = (unsigned)D.c1 * (unsigned)D.c2;
-  y = (int)(idx / (unsigned)D.c2);
-  x = (int)(idx - (unsigned)y * (unsigned)D.c2);
-  ci = (int64_t)zr * plane + idx;
-  return idx < plane;
-}
-__device__ __forceinline__ int64_t block_linear() { return (int64_t)blockIdx.y * gridDim.x + blockIdx.x; }
 
-// corner i of the cell at (z, y, x): Lewiner's numbering (0,0,0) (1,0,0) (1,1,0) (0,1,0) and the same at z+1 --
-// the order of DJ_MC_CORNER, written out so that the eight loads are one base address plus constant offsets
-__device__ __forceinline__ void load_cube(const Dims& D, const float* __restrict__ vol, int zr, int y, int x, double (&f)[8]) {
-  const int64_t sy = D.n2, sz = (int64_t)D.n1 * D.n2;
-  const float* p = vol + ((int64_t)zr * D.n1 + y) * D.n2 + x;
-  const float v[8] = {__ldg(p), __ldg(p + 1), __ldg(p + sy + 1), __ldg(p + sy),
-                      __ldg(p + sz), __ldg(p + sz + 1), __ldg(p + sz + sy + 1), __ldg(p + sz + sy)};
-#pragma unroll
-  for (int i = 0; i < 8; i++) f[i] = __dsub_rn((double)v[i], D.level);
-}
-
-__device__ __forceinline__ int cube_variant(const double (&f)[8]) {
-  int cfg = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) cfg |= (f[i] > 0.0) ? (1 << i) : 0;
+// variant of a cut cell: configuration + Lewiner's test_face on its ambiguous faces.  v: float32 corner values;
+// the differences to the level are formed in float64 (as the sweep does) only for the corners of ambiguous faces
+__device__ __forceinline__ int cube_variant(int cfg, const float (&v)[8], double level) {
   int var = DJ_MC_VARBASE[cfg];
   const int na = DJ_MC_NAMB[cfg];
   for (int a = 0; a < na; a++) {
     const unsigned char* c = DJ_MC_FACE[DJ_MC_AMBFACE[cfg][a]];
-    // Lewiner's test_face: with A, C one diagonal and B, D the other, the corners above the level are joined through
-    // the face when |AC - BD| < FLT_EPSILON (his dead band) or the face-centre saddle (AC - BD) / (A + C - B - D)
-    // is positive; products and difference rounded separately (no fused multiply-add), as the C library computes them
-    const double p02 = __dmul_rn(f[c[0]], f[c[2]]);
-    const double p13 = __dmul_rn(f[c[1]], f[c[3]]);
-    const double det = __dsub_rn(p02, p13);
+    // with A, C one diagonal and B, D the other, the corners above the level are joined through the face when
+    // |AC - BD| < FLT_EPSILON (Lewiner's dead band) or the face-centre saddle (AC - BD) / (A + C - B - D) is
+    // positive; products and difference rounded separately (no fused multiply-add), as the C library computes them
+    const double f0 = __dsub_rn((double)v[c[0]], level), f1 = __dsub_rn((double)v[c[1]], level);
+    const double f2 = __dsub_rn((double)v[c[2]], level), f3 = __dsub_rn((double)v[c[3]], level);
+    const double det = __dsub_rn(__dmul_rn(f0, f2), __dmul_rn(f1, f3));
     const bool joined = (fabs(det) < FLT_EPS_D) || (((cfg >> c[0]) & 1) ? (det > 0.0) : (det < 0.0));
     var += joined ? (1 << a) : 0;
   }
@@ -89,41 +87,22 @@ __device__ __forceinline__ unsigned owned_mask(const Dims& D, int zr, int y, int
   return 0x1FFFu & ~(((zr | D.seam) ? MZ : 0u) | (y ? MY : 0u) | (x ? MX : 0u));
 }
 
-__device__ __forceinline__ int owned_count(int var, unsigned own) {
-  int n = 0;
-  const int ne = DJ_MC_NEDGE[var];
-  for (int k = 0; k < ne; k++) n += (own >> DJ_MC_ORDER[var][k]) & 1u;
-  return n;
-}
+__device__ __forceinline__ int owned_count(int var, unsigned own) { return __popc(own & (unsigned)DJ_MC_EMASK[var]); }
 
-// block-wide exclusive scan of one int per thread (CB threads); returns exclusive prefix, total in *tot
-__device__ __forceinline__ int block_excl_scan(int v, int* smem /*[CB/32]*/, int* tot) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) smem[w] = inc;
-  __syncthreads();
-  if (w == 0) {
-    int s = (lane < CB / 32) ? smem[lane] : 0;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(0xffffffffu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane < CB / 32) smem[lane] = s;
-  }
-  __syncthreads();
-  const int base = w ? smem[w - 1] : 0;
-  *tot = smem[CB / 32 - 1];
-  __syncthreads();
-  return base + inc - v;
-}
+// ---- pass 1: classify every cell, record the cut ones, per-unit counts, min / max.
+// The unit of the scan is a WARP's 31 cells of one row (sweep order: layer, row, chunk): warps never
+// synchronise with each other.  A warp pass handles ROWS consecutive rows at once: ROWS + 1 sample rows of two planes,
+// 2 (ROWS + 1) independent coalesced 128-byte reads in flight per warp, each sample row shared by the two cell rows
+// that touch it; the samples at x + 1 come from the neighbouring lane.
+constexpr int ROWS = 4;
+constexpr int UC = 31;  // cells of a unit: lane 31 of the warp only carries the samples at x + 1 of lane 30's cell
+__device__ __forceinline__ unsigned pack_counts(int n_rec, int nv, int nt) { return (unsigned)n_rec | ((unsigned)nv << 8) | ((unsigned)nt << 20); }
+__device__ __forceinline__ int unpack_nv(unsigned p) { return (int)((p >> 8) & 0xFFFu); }
+__device__ __forceinline__ int unpack_nt(unsigned p) { return (int)(p >> 20); }
+__device__ __forceinline__ unsigned arena_of(int unit) { return ((unsigned)unit * 2654435761u) >> 22; }  // 10 bits: NARENA = 1024
 
-// ---- pass 0 (optional): min / max of the volume for skimage's level-range ValueError
+// min / max of the volume for skimage's level-range ValueError: only needed when NO cell is cut (a cut cell has
+// samples on both sides of the level, so the level is inside the range), i.e. on the error path of dj_mc_count
 __global__ void minmax_kernel(const float* __restrict__ vol, int64_t n, int* __restrict__ mm /*[2] ordered ints*/) {
   float lo = INFINITY, hi = -INFINITY;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -143,52 +122,95 @@ __global__ void minmax_kernel(const float* __restrict__ vol, int64_t n, int* __r
   }
 }
 
-// ---- pass 1: classify every cell; per-block (vertex, triangle) counts (block_counts zeroed by the caller).
-// ~97 % of the cells are not cut by the surface: their path is 8 loads, 8 compares and one 2-byte store -- the
-// float64 differences, the table look-ups and the count atomics are only touched by cut cells.
-__global__ void __launch_bounds__(CB) classify_kernel(Dims D, const float* __restrict__ vol, uint16_t* __restrict__ var_out,
-                                                      int2* __restrict__ block_counts) {
-  int zr, y, x;
-  int64_t ci;
-  int nv = 0, nt = 0;
-  if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
-    const int64_t sy = D.n2, sz = (int64_t)D.n1 * D.n2;
-    const float* p = vol + ((int64_t)zr * D.n1 + y) * D.n2 + x;
-    const float v[8] = {__ldg(p), __ldg(p + 1), __ldg(p + sy + 1), __ldg(p + sy),
-                        __ldg(p + sz), __ldg(p + sz + 1), __ldg(p + sz + sy + 1), __ldg(p + sz + sy)};
-    int cfg = 0;
+__global__ void __launch_bounds__(CB) classify_kernel(Dims D, const float* __restrict__ vol, uint2* __restrict__ units /* zeroed */,
+                                                      Record* __restrict__ records, int arena_cap, int* __restrict__ cursors) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  // grid: x = blocks along the row (8 units each), y = groups of ROWS rows, z = cell layer
+  const int zr = (int)blockIdx.z;
+  const int y0 = (int)blockIdx.y * ROWS;
+  const int xw = (int)blockIdx.x * (CB / 32) + w;  // unit of the row
+  if (xw >= D.wpr) return;
+  const int x = xw * UC + lane;
+  const bool has_sample = x < D.n2, has_cell = lane < UC && x < D.c2;
+  const int64_t sy = D.n2, sz = (int64_t)D.n1 * D.n2;
+  const float* p = vol + ((int64_t)zr * D.n1 + y0) * D.n2 + x;
+  // samples at x: rows y0 .. y0 + ROWS of planes z (k = 0) and z + 1 (k = 1)
+  float a[ROWS + 1][2];
 #pragma unroll
-    for (int i = 0; i < 8; i++) cfg |= ((double)v[i] > D.level) ? (1 << i) : 0;  // == ((double)v - level > 0), exactly
-    if (cfg == 0 || cfg == 255) {
-      var_out[ci] = (uint16_t)(cfg == 0 ? DJ_MC_VAR_EMPTY0 : DJ_MC_VAR_EMPTY255);
-    } else {
-      double f[8];
-#pragma unroll
-      for (int i = 0; i < 8; i++) f[i] = __dsub_rn((double)v[i], D.level);
-      const int var = cube_variant(f);
-      var_out[ci] = (uint16_t)var;
-      nt = DJ_MC_NTRI[var];
-      if (nt) nv = owned_count(var, owned_mask(D, zr, y, x));
-    }
+  for (int r = 0; r <= ROWS; r++) {
+    a[r][0] = 0.f; a[r][1] = 0.f;
+    if (has_sample && y0 + r < D.n1) { a[r][0] = __ldg(p + r * sy); a[r][1] = __ldg(p + sz + r * sy); }
   }
-  if (__any_sync(0xffffffffu, nt != 0)) {
+  // "above the level" flags of my samples: v > level_lo  <=>  sign bit of (level_lo - v) (v == level_lo gives +0).
+  // Bit 2 r + k of `mine`; the flags of the samples at x + 1 come from the next lane in ONE shuffle.
+  unsigned mine = 0u;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      nv += __shfl_xor_sync(0xffffffffu, nv, o);
-      nt += __shfl_xor_sync(0xffffffffu, nt, o);
+  for (int r = ROWS; r >= 0; r--) {
+    mine = __funnelshift_l(__float_as_uint(D.level_lo - a[r][1]), mine, 1);
+    mine = __funnelshift_l(__float_as_uint(D.level_lo - a[r][0]), mine, 1);
+  }
+  const unsigned next = __shfl_down_sync(0xffffffffu, mine, 1);
+#pragma unroll
+  for (int r = 0; r < ROWS; r++) {
+    const int y = y0 + r;
+    if (y >= D.c1) break;  // warp-uniform
+    // flags of the cell's 8 corners: m = mine >> 2r -> bit0 (y, z) bit1 (y, z+1) bit2 (y+1, z) bit3 (y+1, z+1) at x,
+    // n = next >> 2r the same at x + 1.  The cell is cut iff they are not all equal; ~85 % of the units have no
+    // cut cell and stop here.
+    const unsigned m = (mine >> (2 * r)) & 15u, n = (next >> (2 * r)) & 15u;
+    const unsigned all8 = m | (n << 4);
+    const bool cut = has_cell && all8 != 0u && all8 != 255u;
+    const unsigned cutmask = __ballot_sync(0xffffffffu, cut);
+    if (cutmask == 0u) continue;
+    // ---- a unit with cut cells: configuration in Lewiner's corner order (0,0,0) (1,0,0) (1,1,0) (0,1,0) and the
+    // same at z + 1, and the values at x + 1
+    const int cfg = (int)((m & 1u) | ((n & 1u) << 1) | (((n >> 2) & 1u) << 2) | (((m >> 2) & 1u) << 3) |
+                          (((m >> 1) & 1u) << 4) | (((n >> 1) & 1u) << 5) | (((n >> 3) & 1u) << 6) | (((m >> 3) & 1u) << 7));
+    const float b0 = __shfl_down_sync(0xffffffffu, a[r][0], 1), b1 = __shfl_down_sync(0xffffffffu, a[r][1], 1);
+    const float b2 = __shfl_down_sync(0xffffffffu, a[r + 1][0], 1), b3 = __shfl_down_sync(0xffffffffu, a[r + 1][1], 1);
+    const float v[8] = {a[r][0], b0, b2, a[r + 1][0], a[r][1], b1, b3, a[r + 1][1]};
+    int var = 0, nv = 0, nt = 0;
+    if (cut) {
+      var = cube_variant(cfg, v, D.level);
+      nt = DJ_MC_NTRI[var];
+      nv = owned_count(var, owned_mask(D, zr, y, x));
     }
-    if ((threadIdx.x & 31) == 0) {
-      int2* c = block_counts + block_linear();
-      if (nv) atomicAdd(&c->x, nv);
-      atomicAdd(&c->y, nt);
+    const int packed = nv | (nt << 16);
+    int inc = packed;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += t;
+    }
+    const int tot = __shfl_sync(0xffffffffu, inc, 31);
+    const int n_rec = __popc(cutmask);
+    const int unit = (zr * D.c1 + y) * D.wpr + xw;
+    const unsigned arena = arena_of(unit);
+    int base = 0;
+    if (lane == 0) {
+      base = atomicAdd(cursors + arena, n_rec);  // this unit's run inside its arena
+      units[unit] = make_uint2(pack_counts(n_rec, tot & 0xFFFF, tot >> 16), (unsigned)base);
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cut) {
+      const int k = base + __popc(cutmask & ((1u << lane) - 1u));
+      if (k < arena_cap) {  // otherwise the host grows the arenas and classifies again (dj_mc_count)
+        Record rec;
+        rec.cell = (zr * D.c1 + y) * D.c2 + x;
+        rec.unit = unit;
+        rec.var = var;
+        rec.pre = inc - packed;
+#pragma unroll
+        for (int i = 0; i < 8; i++) rec.f[i] = v[i];
+        records[(int64_t)arena * arena_cap + k] = rec;
+      }
     }
   }
 }
 
-// ---- pass 2: exclusive scan of the per-block counts in two levels.
-// level 1: every CTA scans 1024 counts in place (-> offsets within its group) and writes the group total;
-// level 2: one CTA scans the group totals and writes the grand totals for the host.  Consumers add
-// offsets[b] + group_off[b >> 10].
+// ---- pass 2: exclusive scan of the per-unit (vertex, triangle) counts in two levels, sweep order.
+// level 1: every CTA scans 1024 units (-> offsets within its group) and writes the group totals; level 2: one CTA
+// scans the group totals and writes the grand totals for the host.  Consumers add offsets[u] + group_off[u >> 10].
 constexpr int SG = 1024;
 __device__ __forceinline__ void scan1024(long long& a, long long& b, long long (*wsum)[32]) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -214,15 +236,16 @@ __device__ __forceinline__ void scan1024(long long& a, long long& b, long long (
   a = (w ? wsum[0][w - 1] : 0) + a - a0;  // exclusive
   b = (w ? wsum[1][w - 1] : 0) + b - b0;
 }
-__global__ void __launch_bounds__(SG) scan_groups_kernel(const int2* __restrict__ counts, int64_t nblocks, int2* __restrict__ offsets,
+__global__ void __launch_bounds__(SG) scan_groups_kernel(const uint2* __restrict__ units, int64_t nunits, int2* __restrict__ offsets,
                                                          longlong2* __restrict__ group_tot) {
   __shared__ long long wsum[2][32];
   const int64_t i = (int64_t)blockIdx.x * SG + threadIdx.x;
-  const int2 c = (i < nblocks) ? counts[i] : make_int2(0, 0);
-  long long a = c.x, b = c.y;
+  const unsigned pc = (i < nunits) ? units[i].x : 0u;
+  const long long cv = unpack_nv(pc), ct = unpack_nt(pc);
+  long long a = cv, b = ct;
   scan1024(a, b, wsum);
-  if (i < nblocks) offsets[i] = make_int2((int)a, (int)b);
-  if (threadIdx.x == SG - 1) group_tot[blockIdx.x] = make_longlong2(a + c.x, b + c.y);
+  if (i < nunits) offsets[i] = make_int2((int)a, (int)b);
+  if (threadIdx.x == SG - 1) group_tot[blockIdx.x] = make_longlong2(a + cv, b + ct);
 }
 __global__ void __launch_bounds__(SG) scan_totals_kernel(longlong2* __restrict__ group_tot, int64_t ngroups,
                                                          long long* __restrict__ totals) {
@@ -246,6 +269,12 @@ __global__ void __launch_bounds__(SG) scan_totals_kernel(longlong2* __restrict__
 // index of the edge->vertex-id slot of edge e of cell (zr, y, x): 4 slots per sample (x-, y-, z-edge
 // starting at that sample, centre vertex of the cell whose origin it is), samples slab-relative
 constexpr int SLOTS = 4;
+__device__ __forceinline__ void cell_coords(const Dims& D, int cell, int& zr, int& y, int& x) {
+  x = cell % D.c2;
+  const int q = cell / D.c2;
+  y = q % D.c1;
+  zr = q / D.c1;
+}
 __device__ __forceinline__ int64_t edge_slot(const Dims& D, int zr, int y, int x, int e) {
   if (e == 12) return SLOTS * (((int64_t)zr * D.n1 + y) * D.n2 + x) + 3;
   const int a = DJ_MC_EDGE[e][0], b = DJ_MC_EDGE[e][1];
@@ -270,50 +299,31 @@ __device__ __forceinline__ void edge_frac(const double (&f)[8], int e, double (&
   }
 }
 
-// ---- pass 3: vertices (sweep first-use order) + edge -> id table.  One thread per owned vertex.
-constexpr int MAXV = 13;  // owned vertices of one cell: 12 edges + the centre
-__global__ void __launch_bounds__(CB, 4) emit_vertices_kernel(Dims D, const float* __restrict__ vol,
-                                                              const uint16_t* __restrict__ var_in,
-                                                              const int2* __restrict__ block_counts,
-                                                              const int2* __restrict__ block_off,
-                                                              const longlong2* __restrict__ group_off, int* __restrict__ edge_id,
-                                                              float* __restrict__ verts) {
-  __shared__ int sscan[CB / 32];
-  __shared__ uint16_t slist[CB * MAXV];  // (cell's thread << 4) | edge, in id order
-  if (block_counts[block_linear()].x == 0) return;  // most blocks: the surface creates no vertex here
+// ---- pass 3: vertices (ids in sweep first-use order) + edge -> id table.  One thread per cut cell, dense.
+constexpr int EB = 128;  // records per block of the emit kernels
+// thread i <-> entry i % span of arena i / span (span = the fullest arena, rounded up: live if below the arena's cursor)
+__device__ __forceinline__ int64_t live_record(int64_t i, int span, int arena_cap, const int* __restrict__ cursors) {
+  const int a = (int)(i / span), k = (int)(i - (int64_t)a * span);
+  return (a < NARENA && k < __ldg(cursors + a)) ? (int64_t)a * arena_cap + k : -1;
+}
+__global__ void __launch_bounds__(EB) emit_vertices_kernel(Dims D, const Record* __restrict__ records, int span, int arena_cap,
+                                                           const int* __restrict__ cursors, const int2* __restrict__ block_off,
+                                                           const longlong2* __restrict__ group_off, int* __restrict__ edge_id,
+                                                           float* __restrict__ verts) {
+  const int64_t i = live_record((int64_t)blockIdx.x * EB + threadIdx.x, span, arena_cap, cursors);
+  if (i < 0) return;
+  const Record r = records[i];
   int zr, y, x;
-  int64_t ci;
-  int var = 0, nv = 0;
-  unsigned own = 0;
-  if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
-    var = var_in[ci];
-    if (DJ_MC_NTRI[var]) {
-      own = owned_mask(D, zr, y, x);
-      nv = owned_count(var, own);
-    }
-  }
-  int tot;
-  const int pre = block_excl_scan(nv, sscan, &tot);
-  if (tot == 0) return;
-  if (nv) {
-    const int ne = DJ_MC_NEDGE[var];
-    int r = pre;
-    for (int k = 0; k < ne; k++) {
-      const int e = DJ_MC_ORDER[var][k];
-      if ((own >> e) & 1u) slist[r++] = (uint16_t)((threadIdx.x << 4) | e);
-    }
-  }
-  __syncthreads();
-  const int64_t bl = block_linear();
-  const int64_t id0 = (int64_t)block_off[bl].x + group_off[bl >> 10].x;
-  for (int v = threadIdx.x; v < tot; v += CB) {
-    const int ent = slist[v];
-    const int e = ent & 15;
-    int cz, cy, cx;
-    int64_t cci;
-    block_cell(D, ent >> 4, cz, cy, cx, cci);
-    double f[8];
-    load_cube(D, vol, cz, cy, cx, f);
+  cell_coords(D, r.cell, zr, y, x);
+  const unsigned own = owned_mask(D, zr, y, x);
+  int64_t id = (int64_t)block_off[r.unit].x + group_off[r.unit >> 10].x + (r.pre & 0xFFFF);
+  double f[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) f[k] = __dsub_rn((double)r.f[k], D.level);
+  const int ne = DJ_MC_NEDGE[r.var];
+  for (int k = 0; k < ne; k++) {
+    const int e = DJ_MC_ORDER[r.var][k];
+    if (!((own >> e) & 1u)) continue;
     double fr[3];
     if (e == 12) {
       // cell-centre vertex: mean of the cell's edge vertices, accumulated in edge-id order
@@ -333,15 +343,15 @@ __global__ void __launch_bounds__(CB, 4) emit_vertices_kernel(Dims D, const floa
     } else {
       edge_frac(f, e, fr);
     }
-    const int base[3] = {cx, cy, D.z_off + cz};
+    const int base[3] = {x, y, D.z_off + zr};
     float p[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) p[d] = (float)__dadd_rn((double)base[d], fr[d]);
-    const int64_t id = id0 + v;
     verts[3 * id + 0] = p[2];  // (axis0, axis1, axis2)
     verts[3 * id + 1] = p[1];
     verts[3 * id + 2] = p[0];
-    edge_id[edge_slot(D, cz, cy, cx, e)] = (int)id;
+    edge_id[edge_slot(D, zr, y, x, e)] = (int)id;
+    id++;
   }
 }
 
@@ -365,42 +375,23 @@ __global__ void top_plane_kernel(const int* __restrict__ edge_id_plane, int* __r
   }
 }
 
-// ---- pass 4: faces, appended cell by cell in table order.  One thread per triangle.
-constexpr int MAXT = 12;
-static_assert(MAXT >= DJ_MC_MAXTRI, "triangle list capacity");
-__global__ void __launch_bounds__(CB, 4) emit_faces_kernel(Dims D, const uint16_t* __restrict__ var_in,
-                                                           const int2* __restrict__ block_counts,
-                                                           const int2* __restrict__ block_off,
-                                                           const longlong2* __restrict__ group_off,
-                                                           const int* __restrict__ edge_id, int descent, int* __restrict__ faces) {
-  __shared__ int sscan[CB / 32];
-  __shared__ uint16_t slist[CB * MAXT];  // (cell's thread << 4) | triangle index, in face order
-  if (block_counts[block_linear()].y == 0) return;  // most blocks: no triangle
+// ---- pass 4: faces, appended cell by cell in table order.  One thread per cut cell, dense.
+__global__ void __launch_bounds__(EB) emit_faces_kernel(Dims D, const Record* __restrict__ records, int span, int arena_cap,
+                                                        const int* __restrict__ cursors, const int2* __restrict__ block_off,
+                                                        const longlong2* __restrict__ group_off,
+                                                        const int* __restrict__ edge_id, int descent, int* __restrict__ faces) {
+  const int64_t i = live_record((int64_t)blockIdx.x * EB + threadIdx.x, span, arena_cap, cursors);
+  if (i < 0) return;
+  const int cell = records[i].cell, block = records[i].unit, var = records[i].var, pre = records[i].pre;
   int zr, y, x;
-  int64_t ci;
-  int var = 0, nt = 0;
-  if (block_cell(D, threadIdx.x, zr, y, x, ci)) {
-    var = var_in[ci];
-    nt = DJ_MC_NTRI[var];
-  }
-  int tot;
-  const int pre = block_excl_scan(nt, sscan, &tot);
-  if (tot == 0) return;
-  for (int t = 0; t < nt; t++) slist[pre + t] = (uint16_t)((threadIdx.x << 4) | t);
-  __syncthreads();
-  const int64_t bl = block_linear();
-  const int64_t f0 = (int64_t)block_off[bl].y + group_off[bl >> 10].y;
-  for (int v = threadIdx.x; v < tot; v += CB) {
-    const int ent = slist[v];
-    const int t = ent & 15;
-    int cz, cy, cx;
-    int64_t cci;
-    block_cell(D, ent >> 4, cz, cy, cx, cci);
-    const int cvar = var_in[cci];
+  cell_coords(D, cell, zr, y, x);
+  const int64_t f0 = (int64_t)block_off[block].y + group_off[block >> 10].y + (pre >> 16);
+  const int nt = DJ_MC_NTRI[var];
+  for (int t = 0; t < nt; t++) {
     int id[3];
 #pragma unroll
-    for (int k = 0; k < 3; k++) id[k] = edge_id[edge_slot(D, cz, cy, cx, DJ_MC_TRI[cvar][3 * t + k])];
-    int* o = faces + 3 * (f0 + v);
+    for (int k = 0; k < 3; k++) id[k] = edge_id[edge_slot(D, zr, y, x, DJ_MC_TRI[var][3 * t + k])];
+    int* o = faces + 3 * (f0 + t);
     if (descent) { o[0] = id[2]; o[1] = id[1]; o[2] = id[0]; }
     else { o[0] = id[0]; o[1] = id[1]; o[2] = id[2]; }
   }

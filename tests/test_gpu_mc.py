@@ -49,6 +49,19 @@ def test_values_equal_to_level_and_ties():
     assert np.array_equal(f, fo) and np.array_equal(v.view(np.uint32), vo.view(np.uint32))
 
 
+@pytest.mark.parametrize("level", [0.1, np.nextafter(np.float32(0.1), np.float32(1)).item(), float(np.float32(0.1)), -0.3, 1e-40])
+def test_levels_between_float32_values(level):
+    """The kernels classify float32 samples against the largest float32 <= level (exactly the double-precision test
+    `v - level > 0` of the sweep): samples one ulp below / on / above a level that is not a float32 itself."""
+    rng = np.random.default_rng(3)
+    lf = np.float32(level)
+    choices = np.array([lf, np.nextafter(lf, np.float32(-9)), np.nextafter(lf, np.float32(9)), lf - np.float32(1), lf + np.float32(1)], np.float32)
+    vol = choices[rng.integers(0, 5, (9, 11, 40))]
+    v, f = _gpu_mc(vol, level, "ascent")
+    vo, fo = mc_oracle.marching_cubes(vol, level, "ascent")
+    assert np.array_equal(f, fo) and np.array_equal(v.view(np.uint32), vo.view(np.uint32))
+
+
 def test_errors_match_skimage_contract():
     from deepjoin_b200.core import errors
     vol = _fields(16)["sphere"].astype(np.float32)

@@ -539,6 +539,8 @@ def emit(path):
     for _, o in variants:
         rows.append("{%s}" % ",".join(map(str, o + [255] * (13 - len(o)))))
     L.append("DJ_MC_QUAL unsigned char DJ_MC_ORDER[DJ_MC_NVARIANTS][13] = {\n%s};" % ",\n".join(rows))
+    L.append("// per variant: bit e set = edge e (12 = the cell-centre vertex) carries a vertex of this variant")
+    L.append("DJ_MC_QUAL unsigned short DJ_MC_EMASK[DJ_MC_NVARIANTS] = {%s};" % ",".join(str(sum(1 << e for e in o)) for _, o in variants))
     L.append("#endif")
     with open(path, "w") as f:
         f.write("\n".join(L) + "\n")

@@ -5,7 +5,7 @@ import synth_data
 from bench import make_decoder
 from deepjoin_b200.core import reconstruct as R
 dev = torch.device("cuda", 0)
-dec = make_decoder(0, dev, "bf16")
+dec = make_decoder(0, dev, os.environ.get("PREC", "bf16"))
 d = int(os.environ.get("DIMS", "256"))
 vol = R.decode_shape_device(synth_data.trained_code(0).to(dev), dec, (d, d, d), use_net=1, padding=0.1, sigmoid=False).reshape(d, d, d)
 for _ in range(4):
