@@ -272,25 +272,27 @@ def test_tensor_core_adam_loop_tracks_the_fp32_loop():
 
 def test_reconstruct_in_blocks_equals_one_call():
     """The loop continued block by block (DjLatentCfg.iter_offset / total_iterations: what reconstruct() does while the
-    host sampler runs ahead) is the loop in one call: lr step at iterations/2, Adam bias correction, log rows."""
+    host sampler runs ahead) is the loop in one call: lr step at iterations/2, Adam bias correction, log rows.
+    Short horizon: Adam's lr-sized steps amplify the run-to-run order of the atomic accumulations over long runs."""
     from deepjoin_b200 import reconstruct as R
     dec = util.make_decoder(0, "trained_norm", precision="fp32")
     xyz, sdf, nrm = synth.make_sample_set(6000, seed=2)
     px, ps, pn = (torch.from_numpy(a.astype(np.float32)).cuda() for a in (xyz, sdf.reshape(-1), nrm))
-    sched = np.random.default_rng(0).integers(0, 6000, (47, 500)).astype(np.int32)
+    sched = np.random.default_rng(0).integers(0, 6000, (9, 2000)).astype(np.int32)
     code0 = R.init_code(128, 64, 0.01)
-    kw = dict(lr=5e-3, lambda1=1.0, lambda3=1.0, clamp_dist=0.1, l2reg=True)
+    kw = dict(lr=5e-3, lambda1=1.0, lambda3=1.0, clamp_dist=0.1, l2reg=True, log_every=2)
     for prec in ("fp32", "fp16x2"):
         log1, c1 = R.optimize_code(dec, code0, px, ps, pn, torch.from_numpy(sched).cuda(), precision=prec, **kw)
-        log2, c2 = R.optimize_code(dec, code0, px, ps, pn, None, precision=prec, total_iterations=47,
-                                   schedule_blocks=iter([sched[:10], sched[10:11], sched[11:40], sched[40:]]), **kw)
+        log2, c2 = R.optimize_code(dec, code0, px, ps, pn, None, precision=prec, total_iterations=9,
+                                   schedule_blocks=iter([sched[:3], sched[3:4], sched[4:]]), **kw)
         assert log1.shape == log2.shape == (5, 8)
-        # same arithmetic; the atomic accumulations (loss terms, column sums) add in a different order from run to run,
-        # and Adam's lr-sized steps amplify that
-        tol = 2e-4 if prec == "fp32" else 2e-3
-        assert torch.allclose(log1, log2, rtol=1e-3, atol=1e-4) and torch.allclose(c1, c2, atol=tol)
+        assert log1[:, 0].tolist() == [0, 2, 4, 6, 8] == log2[:, 0].tolist()
+        assert torch.allclose(log1, log2, rtol=2e-3, atol=1e-4), (prec, (log1 - log2).abs().max())
+        assert torch.allclose(c1, c2, atol=2e-3), (prec, (c1 - c2).abs().max())
+        # the lr step (x0.1 from iteration int(9/2) = 4) is taken in the right block: a loop without it moves further
+        assert float((c1 - code0.cuda()).abs().max()) < 9 * 5e-3
     with pytest.raises(ValueError):
-        R.optimize_code(dec, code0, px, ps, pn, None, total_iterations=50, schedule_blocks=iter([sched[:10]]), **kw)
+        R.optimize_code(dec, code0, px, ps, pn, None, total_iterations=50, schedule_blocks=iter([sched[:3]]), **kw)
 
 
 def test_reconstruct_follows_decoder_precision():
