@@ -485,6 +485,10 @@ def main():
             if prec == "bf16" and d == 256:
                 # dram__bytes_read.sum + dram__bytes_write.sum of one 256^3 launch (profiles/r01_tc2_forward_256_ncu_full.txt)
                 r["traffic"] = 20361728
+            if prec == "fp16x2" and d == 256:
+                # the same of tc2_forward_kernel<0, 1, 1> (profiles/r02_tc2_forward_fp16x2_256_ncu_full.txt): 12.7 MB read
+                # (two weight streams) + 18.4 MB written of the 67 MB output volume (the rest still in L2 at kernel end)
+                r["traffic"] = 31124480
             return r
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
