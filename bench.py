@@ -404,6 +404,7 @@ def main():
         logs, n_mesh = run_shapes(iters_l)
         l1.record()
         torch.cuda.synchronize()
+        wall_l = time.perf_counter() - wl
         bf_ms = None
         if lat_prec != "bf16":  # the single-pass step on the same shapes / schedule (Adam loop only), for the roofline
             codes0 = torch.cat([RR.init_code(128, 64, 0.01) for _ in range(n_sh)])
@@ -420,7 +421,7 @@ def main():
                                   "rank in one fused forward+backward tensor-core launch per iteration), then one %d^3 restoration "
                                   "mesh per shape (meshes in precision %s)" % (n_sh, iters_l, ns_l, d, args.precision),
                       "shapes_per_s": world * n_sh / (tl * 1e-3), "ms_per_shape": tl / n_sh,
-                      "wall_ms_per_shape": 1e3 * (time.perf_counter() - wl) / n_sh, "meshes_with_surface": n_mesh,
+                      "wall_ms_per_shape": 1e3 * wall_l / n_sh, "meshes_with_surface": n_mesh,
                       "adam_loop_ms_per_shape": run_shapes.opt_ms / n_sh, "schedule_ms_per_shape": run_shapes.sched_ms / n_sh,
                       "mesh_ms_per_shape": run_shapes.mesh_ms / n_sh,
                       "adam_loop_tflops_alg": n_sh * iters_l * ns_l * 11.03e6 / (run_shapes.opt_ms * 1e-3) / 1e12,
