@@ -62,6 +62,8 @@ struct DjPack {
   // split-operand program (DJ_PREC_FP16X2): every K = 128 stage twice (W_hi, W_lo; IEEE half, scaled per layer)
   uint8_t* stream2x[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
   tc2::Net nets2x[2];
+  uint8_t* stream3x[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // three-pass split-operand program
+  tc2::Net nets3x[2];
   unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
   // fused forward+backward program of the latent step (latent_tc2.cuh)
   uint8_t* lat_stream[2] = {nullptr, nullptr};
@@ -120,6 +122,8 @@ static void free_pack(DjPack* p) {
       if (p->stream2h[i][r]) cudaFree(p->stream2h[i][r]);
     for (int r = 0; r < 2; r++)
       if (p->stream2x[i][r]) cudaFree(p->stream2x[i][r]);
+    for (int r = 0; r < 2; r++)
+      if (p->stream3x[i][r]) cudaFree(p->stream3x[i][r]);
   }
   if (p->bias_dev) cudaFree(p->bias_dev);
   for (int r = 0; r < 2; r++) {
@@ -497,6 +501,74 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       N.stream[r] = p->stream2x[net][r];
     }
   }
+  // ---- three-pass split-operand program (tc2_forward_kernel<.., 2>): 128 x 256 x 16 MMAs, 256 output columns per
+  // accumulator chunk (128 weight rows per CTA), one ring stage = one [128 x 64] tile; per K range and k-chunk the
+  // W_lo tile, then the W_hi tile
+  for (int net = 0; net < 2; net++) {
+    const int nl = net == 0 ? d->f_layers : d->h_layers;
+    const float* const* W = net == 0 ? f_w : h_w;
+    const std::vector<int>& outs = net == 0 ? p->f_out : p->h_out;
+    const std::vector<int>& ins = net == 0 ? p->f_in : p->h_in;
+    tc2::Net& N = p->nets3x[net];
+    N = p->nets2x[net];
+    std::vector<uint8_t> blob[2];
+    {
+      tc2::Layer& T = N.layers[0];
+      const float sc = 1.f / T.inv_scale;
+      T.n_chunks = 2; T.mma_n = 256; T.tile_bytes = 128 * 128; T.stage_bytes = T.tile_bytes;
+      const int xyz_off = (net == 0 ? L : Lb);
+      for (int j = 0; j < 2; j++)
+        for (int r = 0; r < 2; r++) {
+          const size_t o = blob[r].size();
+          blob[r].resize(o + T.tile_bytes);
+          pack_tile_l0_x2(W[0], ins[0], xyz_off, j * 256 + r * 128, 128, blob[r].data() + o, sc);
+        }
+    }
+    for (int l = 1; l < nl; l++) {
+      tc2::Layer& T = N.layers[l];
+      const bool head = (l == nl - 1);
+      const bool reinj = (net == 0 && l == li);
+      const int n_real = outs[l];
+      const int k_real = reinj ? K3 : ins[l];
+      const float sc = 1.f / T.inv_scale;
+      const int k_ranges = T.k_ranges;
+      if (k_ranges > 4) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K=%d exceeds 512 (three-pass program)", l, k_real));
+      T.mma_n = (int16_t)(head ? 32 : 256);
+      T.n_chunks = (int16_t)(head ? 1 : (n_real + 255) / 256);
+      if (T.n_chunks > 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: width %d exceeds 512 (three-pass program)", l, n_real));
+      if (T.n_chunks > 1 && k_ranges < 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K=%d below 129 (three-pass program)", l, k_real));
+      T.k_steps = 4;
+      T.k_stages = (int16_t)(4 * k_ranges);
+      const int rows = T.mma_n / 2;
+      T.tile_bytes = rows * 128;
+      T.stage_bytes = T.tile_bytes;
+      // K range order: chunk 0 in the order the previous layer's drains publish them; chunk 1 reads range 1 first
+      // so that the drain of chunk 0 may overwrite it early (R1_FREE)
+      std::vector<int> order[2];
+      for (int r = 0; r < k_ranges; r++) order[0].push_back(r);
+      if (k_ranges > 1) order[1].push_back(1);
+      for (int r = 0; r < k_ranges; r++)
+        if (r != 1) order[1].push_back(r);
+      for (int c = 0; c < 2; c++) {
+        T.korder[c] = 0;
+        for (size_t i = 0; i < order[c].size(); i++) T.korder[c] |= (uint32_t)order[c][i] << (4 * i);
+      }
+      for (int j = 0; j < T.n_chunks; j++)
+        for (int r : order[j == 0 ? 0 : 1])
+          for (int kc = 0; kc < 2; kc++)
+            for (int part = 1; part >= 0; part--)
+              for (int c = 0; c < 2; c++) {
+                const size_t o = blob[c].size();
+                blob[c].resize(o + T.tile_bytes);
+                pack_tile_x2(W[l], ins[l], n_real, k_real, j * T.mma_n + c * rows, r * 128 + kc * 64, rows, blob[c].data() + o, sc, part);
+              }
+    }
+    for (int r = 0; r < 2; r++) {
+      DJ_TRY(cudaMalloc((void**)&p->stream3x[net][r], blob[r].size()));
+      DJ_TRY(cudaMemcpy(p->stream3x[net][r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
+      N.stream[r] = p->stream3x[net][r];
+    }
+  }
   // ---- latent-step program (latent_tc2.cuh): forward, loss, backward in one pass over the tile
   {
     const int nlf = d->f_layers, nlh = d->h_layers;
@@ -756,8 +828,15 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
     const bool x2 = precision == DJ_PREC_FP16X2;
     tc2::Params P;
     memset(&P, 0, sizeof P);
-    P.nets[0] = x2 ? p->nets2x[0] : p->nets2[0];
-    P.nets[1] = x2 ? p->nets2x[1] : p->nets2[1];
+    // DJ_PREC_FP16X2 runs the three-pass program; DEEPJOIN_B200_X2_FOURPASS=1 selects the four-pass one (diagnostics)
+#ifdef DJ_DEBUG
+    const bool four_pass = getenv("DEEPJOIN_B200_X2_FOURPASS") != nullptr;
+#else
+    static const bool four_pass = getenv("DEEPJOIN_B200_X2_FOURPASS") != nullptr;
+#endif
+    const bool x3 = x2 && !four_pass;
+    P.nets[0] = x3 ? p->nets3x[0] : (x2 ? p->nets2x[0] : p->nets2[0]);
+    P.nets[1] = x3 ? p->nets3x[1] : (x2 ? p->nets2x[1] : p->nets2[1]);
     if (f16)
       for (int net = 0; net < 2; net++)
         for (int r = 0; r < 2; r++) P.nets[net].stream[r] = p->stream2h[net][r];
@@ -787,9 +866,22 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
 #endif
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       p->tc_attr_set2 = true;
     }
-    if (x2) tc2::tc2_forward_kernel<0, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+#ifdef DJ_DEBUG
+    if (x2 && (P.debug & 64)) DJ_CUDA(cudaMemsetAsync(p->prof, 0, 64 * sizeof(unsigned long long), st));
+    if (x2 && !x3 && P.debug) {
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      tc2::tc2_forward_kernel<1, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    } else
+    if (x3 && P.debug) {
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      tc2::tc2_forward_kernel<1, 1, 2><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    } else
+#endif
+    if (x3) tc2::tc2_forward_kernel<0, 1, 2><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    else if (x2) tc2::tc2_forward_kernel<0, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
 #ifdef DJ_DEBUG
     else if (P.debug) tc2::tc2_forward_kernel<1, 0><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);

@@ -57,6 +57,13 @@ constexpr int NSTAGES_X2 = 4;
 constexpr int SM_X = SM_W + NSTAGES_X2 * STAGE_BYTES;  // 16 KB: 4 warp pairs x 32 lanes x 32 words
 constexpr int TILE_PTS_X2 = 64;
 
+// three-pass split-operand mode (X2 = 2): the 128 KB activation area holds the four K ranges of a layer's input as
+// separate 64-row a_hi / a_lo tiles (16 KB each: two [64 x 64] k-chunks), K range R at R * 32 KB, single-buffered
+constexpr int X3_TILE = 64 * KCH * 2;          // 8 KB: one [64 rows x 64] k-chunk
+constexpr int X3_PART = 2 * X3_TILE;           // 16 KB: a_hi (or a_lo) of one K range
+constexpr int X3_RANGE = 2 * X3_PART;          // 32 KB: a_hi + a_lo of one K range
+constexpr int X3_NCHUNK = 256;                 // output columns per accumulator chunk (N of the MMA)
+
 constexpr uint32_t TM_A = 0;      // TMEM columns [0,256): bf16 activations (A operand of odd layers)
 constexpr uint32_t TM_ACC = 256;  // TMEM columns [256,512): two fp32 accumulator buffers
 
@@ -155,7 +162,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + SM_BAR + 8 * (2 * NSTAGES + 12));
   static_assert(8 * (2 * NSTAGES + 12) + 4 <= 256, "barrier block");
 
-  constexpr int NST = X2 ? NSTAGES_X2 : NSTAGES;          // ring depth
+  constexpr int NST = X2 == 1 ? NSTAGES_X2 : NSTAGES;     // ring depth
   constexpr int TILE_PTS = X2 ? TILE_PTS_X2 : TILE_M;    // points per CTA and pass
   const uint32_t sX = base + SM_X;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,7 +183,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       ptx::mbar_init(W_FULL(s), rank == 0 ? 2 : 1);  // leader: own copy + the peer's relay
       ptx::mbar_init(W_EMPTY(s), 1);
     }
-    for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(0, c), 2 * EPI_WARPS);
+    if constexpr (X2 == 2) {
+      // A_READY(0, r): K range r of the next layer's operand is written (4 warps per CTA own a range);
+      // A_READY(1, r), r = 0, 1 = "R_FREE(r)": the last MMAs that read K range r of the current layer's operand are
+      // done (tcgen05.commit), the drain of chunk 0 may overwrite it
+      for (int c = 0; c < 4; c++) ptx::mbar_init(A_READY(0, c), EPI_WARPS);
+      for (int c = 0; c < 2; c++) ptx::mbar_init(A_READY(1, c), 1);
+    } else {
+      for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(0, c), 2 * EPI_WARPS);
+    }
     for (int i = 0; i < 2; i++) {
       ptx::mbar_init(ACC_FULL(i), 1);
       ptx::mbar_init(ACC_EMPTY(i), 2 * EPI_WARPS);
@@ -238,6 +253,93 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
     if (prof && lane == 0) { pc[11] = tick() - t_begin; pc[12] = w0; }
   } else if (warp == 1) {
     // ===================== leader: MMA issuer for the pair =====================
+    if constexpr (X2 == 2) {
+      // Three-pass split-operand program: every MMA is 128 x 256 x 16 over the pair (64 rows per CTA -- the a_hi OR
+      // the a_lo tile of the CTA's 64 points -- against 128 weight rows per CTA).  Per K range and 64-wide k-chunk:
+      // one ring stage of W_lo (4 MMAs with a_hi) and one of W_hi (4 MMAs with a_hi, 4 with a_lo), all into the same
+      // accumulator: a_hi.W_lo + a_hi.W_hi + a_lo.W_hi.  All operands come from shared memory (an A operand in tensor
+      // memory would have to be present in both lane halves for this shape: the lanes [64,128) that accumulate output
+      // columns [128,256) read their own copy -- tools/x3_diag.py blocks).  Chunk 1 of a layer reads K range 1, then
+      // range 0, first and commits R_FREE(1), R_FREE(0): the drain of chunk 0, which runs meanwhile, overwrites
+      // exactly these two ranges with the next layer's.
+      const uint64_t desc_hi = ptx::umma_desc_sw128_kmajor(0);
+      const uint64_t a_desc0 = desc_hi + (uint64_t)((sA & 0x3FFFF) >> 4);
+      const uint64_t b_desc0 = desc_hi + (uint64_t)((sW & 0x3FFFF) >> 4);
+      uint32_t stage = 0, phase = 0, a_ph = 0, acc_it = 0;
+      auto next_stage = [&]() { if (++stage == NST) { stage = 0; phase ^= 1; } };
+      for (int64_t it = 0; it < iters; it++) {
+        for (int net = 0; net < 2; net++) {
+          if (!((P.net_mask >> net) & 1)) continue;
+          const Net& N = P.nets[net];
+          const int nl = N.n_layers;
+          for (int l = 0; l < nl; l++) {
+            const int n_chunks = N.layers[l].n_chunks, k_steps = N.layers[l].k_steps, k_ranges = N.layers[l].k_ranges;
+            const uint32_t korder0 = N.layers[l].korder[0], korder1 = N.layers[l].korder[1];
+            const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)N.layers[l].mma_n);
+            for (int j = 0; j < n_chunks; j++) {
+              const uint32_t buf = acc_it & 1u;
+              ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u);
+              acc_it++;
+              // two accumulators per chunk: the a_hi.W_hi products go to `d_tmem`, the two small ones (2^-11 of it)
+              // to `d_small`, and the drain adds them in fp32.  tcgen05.mma truncates every accumulation at the
+              // accumulator's exponent (~0.46 ulp per MMA, toward zero): kept apart, the 64 small MMAs cost nothing
+              // and only the 32 large ones contribute, as in the four-pass program.
+              const uint32_t d_tmem = tmem_base + buf * 256u, d_small = d_tmem + 128u;
+              if (k_steps == 1) {  // layer 0: one K = 16 MMA per chunk, operand in the first 32 B of the a_hi rows
+                if (j == 0) ptx::mbar_spin_cluster(A_READY(0, 0), a_ph & 1u);
+                ptx::mbar_spin_cluster(W_FULL(stage), phase);
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
+                  ptx::mma2_f16_ss(d_tmem, a_desc0, b_desc0 + (uint64_t)(stage * (STAGE_BYTES >> 4)), idesc, 0u);
+                  ptx::mma2_commit(W_EMPTY(stage), 3);
+                  ptx::mma2_commit(ACC_FULL(buf), 3);
+                  if (j == 1) { ptx::mma2_commit(A_READY(1, 0), 3); ptx::mma2_commit(A_READY(1, 1), 3); }
+                }
+                __syncwarp();
+                next_stage();
+                continue;
+              }
+              const uint32_t korder = j == 0 ? korder0 : korder1;
+#pragma unroll 1
+              for (int ri = 0; ri < k_ranges; ri++) {
+                const int r = (int)((korder >> (4 * ri)) & 15u);
+                if (j == 0) ptx::mbar_spin_cluster(A_READY(0, r), (a_ph >> r) & 1u);
+                const uint32_t a_off = (uint32_t)(r * X3_RANGE);
+#pragma unroll 1
+                for (int kc = 0; kc < 2; kc++) {
+                  const uint32_t st0 = stage, ph0 = phase;
+                  next_stage();
+                  const uint32_t st1 = stage, ph1 = phase;
+                  next_stage();
+                  ptx::mbar_spin_cluster(W_FULL(st0), ph0);
+                  ptx::mbar_spin_cluster(W_FULL(st1), ph1);
+                  ptx::tc_fence_after();
+                  if (ptx::elect_one()) {
+                    const uint64_t b_lo = b_desc0 + (uint64_t)(st0 * (STAGE_BYTES >> 4)), b_hi = b_desc0 + (uint64_t)(st1 * (STAGE_BYTES >> 4));
+                    const uint32_t first = (uint32_t)((ri | kc) != 0);
+                    const uint64_t ad_hi = a_desc0 + (uint64_t)((a_off + (uint32_t)(kc * X3_TILE)) >> 4), ad_lo = ad_hi + (uint64_t)(X3_PART >> 4);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) ptx::mma2_f16_ss(d_small, ad_hi + (uint64_t)(2 * k), b_lo + (uint64_t)(2 * k), idesc, k ? 1u : first);
+                    ptx::mma2_commit(W_EMPTY(st0), 3);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) ptx::mma2_f16_ss(d_small, ad_lo + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, 1u);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) ptx::mma2_f16_ss(d_tmem, ad_hi + (uint64_t)(2 * k), b_hi + (uint64_t)(2 * k), idesc, k ? 1u : first);
+                    ptx::mma2_commit(W_EMPTY(st1), 3);
+                    if (ri + 1 == k_ranges && kc == 1) ptx::mma2_commit(ACC_FULL(buf), 3);
+                    // chunk 1 reads K ranges 1, 0 first: once they are done the drain of chunk 0 may overwrite them
+                    if (j == 1 && ri < 2 && kc == 1) ptx::mma2_commit(A_READY(1, r), 3);
+                  }
+                  __syncwarp();
+                }
+              }
+              if (j == 0) a_ph ^= (1u << k_ranges) - 1u;
+            }
+            if (k_steps == 1) a_ph ^= 1u;
+          }
+        }
+      }
+    } else {
     // The whole warp walks the (warp-uniform) issue program; one elected lane issues tcgen05.mma /
     // tcgen05.commit.  GEMM layer l of a net reads its A operand from shared memory when l is even
     // (layer 0 wrote it there) and from tensor memory when l is odd; accumulator buffers alternate.
@@ -337,6 +439,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       }
     }
     if (prof && lane == 0) { pc[0] = tick() - t_begin; pc[1] = w1; pc[2] = w2; pc[3] = w3; }
+    }
   } else if constexpr (X2 == 0) {
     // ===================== epilogue: 8 warps; thread = (row, 64-column half of the chunk) ==========
     const int q = warp & 3;              // TMEM lane quarter this warp may access
@@ -516,7 +619,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       if (h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
     }
     if (prof && warp == 2 && lane == 0) { pc[4] = tick() - t_begin; pc[5] = w0; pc[6] = w1; pc[7] = w2; pc[8] = w3; }
-  } else {
+  } else if constexpr (X2 == 1) {
     // ===================== epilogue, split-operand mode (X2) ==========
     // TMEM lane quarter q = warp % 4: quarters 0, 1 hold the a_hi rows of the tile's 64 points ("high" warps),
     // quarters 2, 3 the a_lo rows of the same points ("low" warps).  High warp (q, h) and low warp (q + 2, h) drain
@@ -713,6 +816,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                     v[2 * f + 1] = fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u));
                   }
                 }
+                if (DBG && (debug & 64)) {  // per-layer checksum of the activations (tools/x3_diag.py)
+                  float cs = 0.f, cw = 0.f;
+#pragma unroll
+                  for (int f = 0; f < 8; f++) { cs += v[f]; cw += v[f] * (float)(col0 + gq * 8 + f + 1); }
+                  atomicAdd(reinterpret_cast<double*>(P.prof) + net * 16 + l, (double)cs);
+                  atomicAdd(reinterpret_cast<double*>(P.prof) + 32 + net * 16 + l, (double)cw);
+                }
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
                   const uint32_t ph = ptx::pack_f16x2(v[2 * f], v[2 * f + 1]);
@@ -763,6 +873,217 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       if (!lo_warp && h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
     }
     if (lo_warp) ptx::bar_sync_n(B_FREE, 64);  // consume the last hand-back so that no barrier is left half-arrived
+  } else {
+    // ===================== epilogue, three-pass split-operand mode (X2 = 2) ==========
+    // An accumulator chunk is 64 points x 256 output columns: TMEM lanes [0,64) hold columns [0,128) of the chunk,
+    // lanes [64,128) columns [128,256) (the 128 x 256 cta_group::2 accumulator layout, tools/probe_m128).  Warp
+    // (q = warp % 4, h): points 32 (q & 1) .. + 31, columns 128 (q >> 1) + 64 h .. + 63 of the chunk -- every warp
+    // holds complete sums, applies scale / bias / LeakyReLU, splits the result into a_hi + a_lo and writes both into
+    // the shared-memory tiles of K range R = 2 j + (q >> 1), k-chunk h of the next layer's operand.  Ranges 0 and 1
+    // (drain of chunk 0) are still being read by this layer's chunk 1: their stores wait for R_FREE(R); ranges 2 and
+    // 3 are written by the layer's last drain, when nothing reads the old ones any more.
+    const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
+    const int half = q >> 1;
+    const int prow = (q & 1) * 32 + lane;  // point of the tile, 0..63
+    const int et = threadIdx.x - 64;
+    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t row_off = (uint32_t)(prow * 128);
+    const int sw = prow & 7;
+    const float slope = P.head.slope;
+    const uint64_t slope2 = ptx::pack_f32x2(slope, slope);
+    const uint32_t lead_aready0 = ptx::mapa(A_READY(0, 0), 0);
+    const uint32_t lead_accempty0 = ptx::mapa(ACC_EMPTY(0), 0);
+    const uint32_t R_FREE = A_READY(1, half);
+    uint32_t acc_it = 0, rf_ph = 0;
+    int bias_buf = 0;
+
+    for (int64_t it = 0; it < iters; it++) {
+      const int64_t tile = it * gridDim.x + blockIdx.x;
+      const int64_t g = tile * TILE_PTS + prow;
+      float x = 0.f, y = 0.f, z = 0.f;
+      if (g < P.n) {
+        if (P.grid_mode) grid_point(P, P.r_lo + g, x, y, z);
+        else { x = __ldg(P.xyz + 3 * g); y = __ldg(P.xyz + 3 * g + 1); z = __ldg(P.xyz + 3 * g + 2); }
+      }
+      float yc[5] = {0, 0, 0, 0, 0}, yt[5] = {0, 0, 0, 0, 0};
+
+      for (int net = 0; net < 2; net++) {
+        if (!((P.net_mask >> net) & 1)) continue;
+        const Net& N = P.nets[net];
+        // ---- layer 0: K = 16 operand [p_hi | p_lo | p_hi | 0] in the first 32 B of the point's a_hi row of K range 0
+        // (buffer 0); the tiles hold [W_hi | W_hi | W_lo]
+        tc::epi_bar();  // everybody is past the previous use of sBias
+        {
+          const float4* t = P.tables + N.l0_table * 512;
+          reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = make_float2(__ldg(&t[2 * et].w), __ldg(&t[2 * et + 1].w));
+        }
+        if (half == 0) {
+          if (h == 0) {
+            float hi[3], lo[3];
+            const float p3[3] = {x, y, z};
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              hi[i] = ptx::round_op16<1>(p3[i]);
+              lo[i] = p3[i] - hi[i];
+            }
+            const float k[16] = {hi[0], hi[1], hi[2], lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) w[i] = ptx::pack_op16x2<1>(k[2 * i], k[2 * i + 1]);
+            const uint32_t my_row = sA + row_off;
+            tc::st_shared_v4(my_row + ((0 ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            tc::st_shared_v4(my_row + ((1 ^ sw) << 4), w[4], w[5], w[6], w[7]);
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0);  // K range 0 is owned by the quarters 0, 1
+        }
+
+        for (int l = 0; l < N.n_layers; l++) {
+          const Layer L = N.layers[l];
+          const float inv = L.inv_scale;
+          if (L.kind == KIND_HEAD) {
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l);
+            acc_it++;
+            ptx::tc_fence_after();
+            uint32_t r[8], rs[8];
+            if (half == 0 && h == 0) {
+              ptx::tmem_ld8(tmem_lane + buf * 256u, r);
+              ptx::tmem_ld8(tmem_lane + buf * 256u + 128u, rs);
+              ptx::tmem_wait_ld();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
+            if (half == 0 && h == 0) {
+              float* dst = net == 0 ? yc : yt;
+#pragma unroll
+              for (int i = 0; i < 5; i++) {
+                const float v = fmaf(__uint_as_float(r[i]) + __uint_as_float(rs[i]), inv, __ldg(P.bias + L.bias_off + i));
+                dst[i] = N.head_leaky ? tc::leaky(v, slope) : v;
+              }
+            }
+            continue;
+          }
+          tc::epi_bar();
+          const int next_kind = (l + 1 < N.n_layers) ? N.layers[l + 1].kind : -1;
+          const int next_kr = (l + 1 < N.n_layers) ? N.layers[l + 1].k_ranges : 0;
+          float2 pre_b = make_float2(0.f, 0.f);
+          float4 pre_t0 = make_float4(0, 0, 0, 0), pre_t1 = pre_t0;
+          if (next_kind == KIND_HIDDEN) {
+            pre_b = __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[l + 1].bias_off) + et);
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            const float4* t = P.tables + N.layers[l + 1].table * 512;
+            pre_t0 = __ldg(t + et);
+            pre_t1 = __ldg(t + et + 256);
+          }
+          const float* bias = sBias + bias_buf * 512;
+          const uint64_t inv2 = ptx::pack_f32x2(inv, inv);
+
+          auto drain = [&](auto kind_c, int j) {
+            constexpr int KIND = decltype(kind_c)::value;
+            const uint32_t buf = acc_it & 1u;
+            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j);
+            acc_it++;
+            ptx::tc_fence_after();
+            uint32_t r[64];
+            ptx::tmem_ld64(tmem_lane + buf * 256u + h * 64, r);
+            if (L.k_steps != 1) {  // + the accumulator of the small products (layer 0 is a single MMA)
+              uint32_t rs[64];
+              ptx::tmem_ld64(tmem_lane + buf * 256u + 128u + h * 64, rs);
+              ptx::tmem_wait_ld();
+#pragma unroll
+              for (int i = 0; i < 64; i += 2) {
+                const uint64_t t = ptx::add_f32x2((uint64_t)r[i] | ((uint64_t)r[i + 1] << 32), (uint64_t)rs[i] | ((uint64_t)rs[i + 1] << 32));
+                r[i] = (uint32_t)t;
+                r[i + 1] = (uint32_t)(t >> 32);
+              }
+            } else {
+              ptx::tmem_wait_ld();
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);  // accumulator buffer is free again
+            const int R = 2 * j + half;  // K range of the next layer this warp produces (k-chunk h of it)
+            const bool wait_free = j == 0 && L.n_chunks > 1;
+            if (R >= next_kr) {  // padding columns: the next layer has no such K range
+              if (wait_free) rf_ph ^= 1u;
+              return;
+            }
+            const int col0 = j * X3_NCHUNK + half * 128 + h * 64;
+            const uint32_t dst_hi = sA + (uint32_t)(R * X3_RANGE + h * X3_TILE) + row_off;
+            uint32_t ph[32], pl[32];
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) {
+              float v[8];
+              if (KIND == KIND_HIDDEN_XYZ) {
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                  const float4 t0 = sTab[col0 + gq * 8 + 2 * f], t1 = sTab[col0 + gq * 8 + 2 * f + 1];
+                  const float s0 = fmaf(t0.x, x, fmaf(t0.y, y, fmaf(t0.z, z, t0.w)));
+                  const float s1 = fmaf(t1.x, x, fmaf(t1.y, y, fmaf(t1.z, z, t1.w)));
+                  v[2 * f] = tc::leaky(fmaf(__uint_as_float(r[gq * 8 + 2 * f]), inv, s0), slope);
+                  v[2 * f + 1] = tc::leaky(fmaf(__uint_as_float(r[gq * 8 + 2 * f + 1]), inv, s1), slope);
+                }
+              } else {
+                const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
+                const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8 + 4);
+                const uint64_t bb[4] = {ptx::pack_f32x2(b0.x, b0.y), ptx::pack_f32x2(b0.z, b0.w),
+                                        ptx::pack_f32x2(b1.x, b1.y), ptx::pack_f32x2(b1.z, b1.w)};
+#pragma unroll
+                for (int f = 0; f < 4; f++) {
+                  const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
+                  const uint64_t t = ptx::fma_f32x2(acc, inv2, bb[f]);
+                  const uint64_t u = ptx::mul_f32x2(t, slope2);
+                  v[2 * f] = fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u));
+                  v[2 * f + 1] = fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u));
+                }
+              }
+              if (DBG && (debug & 64)) {  // per-layer checksum of the activations (tools/x3_diag.py)
+                float cs = 0.f, cw = 0.f;
+#pragma unroll
+                for (int f = 0; f < 8; f++) { cs += v[f]; cw += v[f] * (float)(col0 + gq * 8 + f + 1); }
+                atomicAdd(reinterpret_cast<double*>(P.prof) + net * 16 + l, (double)cs);
+                atomicAdd(reinterpret_cast<double*>(P.prof) + 32 + net * 16 + l, (double)cw);
+              }
+#pragma unroll
+              for (int f = 0; f < 4; f++) {
+                ph[gq * 4 + f] = ptx::pack_f16x2(v[2 * f], v[2 * f + 1]);
+                const float2 back = ptx::f16x2_to_float2(ph[gq * 4 + f]);
+                pl[gq * 4 + f] = ptx::pack_f16x2(v[2 * f] - back.x, v[2 * f + 1] - back.y);
+              }
+            }
+            if (wait_free) {  // the MMAs of chunk 1 that still read the old K range R
+              ptx::mbar_wait(R_FREE, rf_ph, P.err, 0x680 | l);
+              rf_ph ^= 1u;
+            }
+#pragma unroll
+            for (int gq = 0; gq < 8; gq++) {
+              const uint32_t d = dst_hi + ((gq ^ sw) << 4);
+              tc::st_shared_v4(d, ph[gq * 4], ph[gq * 4 + 1], ph[gq * 4 + 2], ph[gq * 4 + 3]);
+              tc::st_shared_v4(d + X3_PART, pl[gq * 4], pl[gq * 4 + 1], pl[gq * 4 + 2], pl[gq * 4 + 3]);
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(lead_aready0 + 8u * R);
+          };
+          using I0 = std::integral_constant<int, 0>;
+          using I1 = std::integral_constant<int, 1>;
+          if (L.kind == KIND_HIDDEN_XYZ) for (int j = 0; j < L.n_chunks; j++) drain(I1{}, j);
+          else for (int j = 0; j < L.n_chunks; j++) drain(I0{}, j);
+          if (next_kind == KIND_HIDDEN) {
+            bias_buf ^= 1;
+            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = pre_b;
+          } else if (next_kind == KIND_HIDDEN_XYZ) {
+            sTab[et] = pre_t0;
+            sTab[et + 256] = pre_t1;
+          }
+        }
+      }
+      if (half == 0 && h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
+    }
   }
 
   ptx::tc_fence_before();
