@@ -278,7 +278,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             const uint32_t idesc = ptx::umma_idesc_f16(128, (uint32_t)N.layers[l].mma_n);
             for (int j = 0; j < n_chunks; j++) {
               const uint32_t buf = acc_it & 1u;
-              ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u);
+              { const long long t = tick(); ptx::mbar_spin_cluster(ACC_EMPTY(buf), ((acc_it >> 1) & 1u) ^ 1u); w1 += tick() - t; }
               acc_it++;
               // two accumulators per chunk: the a_hi.W_hi products go to `d_tmem`, the two small ones (2^-11 of it)
               // to `d_small`, and the drain adds them in fp32.  tcgen05.mma truncates every accumulation at the
@@ -303,7 +303,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
 #pragma unroll 1
               for (int ri = 0; ri < k_ranges; ri++) {
                 const int r = (int)((korder >> (4 * ri)) & 15u);
-                if (j == 0) ptx::mbar_spin_cluster(A_READY(0, r), (a_ph >> r) & 1u);
+                if (j == 0) { const long long t = tick(); ptx::mbar_spin_cluster(A_READY(0, r), (a_ph >> r) & 1u); w2 += tick() - t; }
                 const uint32_t a_off = (uint32_t)(r * X3_RANGE);
 #pragma unroll 1
                 for (int kc = 0; kc < 2; kc++) {
@@ -311,8 +311,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                   next_stage();
                   const uint32_t st1 = stage, ph1 = phase;
                   next_stage();
-                  ptx::mbar_spin_cluster(W_FULL(st0), ph0);
-                  ptx::mbar_spin_cluster(W_FULL(st1), ph1);
+                  { const long long t = tick(); ptx::mbar_spin_cluster(W_FULL(st0), ph0); ptx::mbar_spin_cluster(W_FULL(st1), ph1); w3 += tick() - t; }
                   ptx::tc_fence_after();
                   if (ptx::elect_one()) {
                     const uint64_t b_lo = b_desc0 + (uint64_t)(st0 * (STAGE_BYTES >> 4)), b_hi = b_desc0 + (uint64_t)(st1 * (STAGE_BYTES >> 4));
@@ -339,6 +338,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
           }
         }
       }
+      if (prof && lane == 0) { pc[0] = tick() - t_begin; pc[1] = w1; pc[2] = w2; pc[3] = w3; }
     } else {
     // The whole warp walks the (warp-uniform) issue program; one elected lane issues tcgen05.mma /
     // tcgen05.commit.  GEMM layer l of a net reads its A operand from shared memory when l is even
@@ -945,7 +945,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
           const float inv = L.inv_scale;
           if (L.kind == KIND_HEAD) {
             const uint32_t buf = acc_it & 1u;
-            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l);
+            { const long long t = tick(); ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x500 | l); w3 += tick() - t; }
             acc_it++;
             ptx::tc_fence_after();
             uint32_t r[8], rs[8];
@@ -979,26 +979,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             pre_t0 = __ldg(t + et);
             pre_t1 = __ldg(t + et + 256);
           }
-          const float* bias = sBias + bias_buf * 512;
+          const uint32_t bias_s = base + SM_BIAS + (uint32_t)(bias_buf * 2048);
           const uint64_t inv2 = ptx::pack_f32x2(inv, inv);
 
           auto drain = [&](auto kind_c, int j) {
             constexpr int KIND = decltype(kind_c)::value;
             const uint32_t buf = acc_it & 1u;
-            ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j);
+            const int col0 = j * X3_NCHUNK + half * 128 + h * 64;
+            // the first half of this warp's bias values is fetched while the accumulator is still being computed: the
+            // tensor core's operand reads keep the shared-memory pipe busy, a load issued inside the drain waits long
+            uint32_t bpre[32];
+            if (KIND != KIND_HIDDEN_XYZ) {
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                ptx::ld_shared_v4u(bias_s + (uint32_t)((col0 + 4 * i) * 4), bpre[4 * i], bpre[4 * i + 1], bpre[4 * i + 2], bpre[4 * i + 3]);
+            }
+            { const long long t = tick(); ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j); w0 += tick() - t; }
             acc_it++;
             ptx::tc_fence_after();
             uint32_t r[64];
             ptx::tmem_ld64(tmem_lane + buf * 256u + h * 64, r);
-            if (L.k_steps != 1) {  // + the accumulator of the small products (layer 0 is a single MMA)
-              uint32_t rs[64];
-              ptx::tmem_ld64(tmem_lane + buf * 256u + 128u + h * 64, rs);
-              ptx::tmem_wait_ld();
+            if (L.k_steps != 1) {  // + the accumulator of the small products (layer 0 is a single MMA); in two halves:
+              // 64 + 64 live accumulator registers do not fit next to the rest (168 registers per thread)
 #pragma unroll
-              for (int i = 0; i < 64; i += 2) {
-                const uint64_t t = ptx::add_f32x2((uint64_t)r[i] | ((uint64_t)r[i + 1] << 32), (uint64_t)rs[i] | ((uint64_t)rs[i + 1] << 32));
-                r[i] = (uint32_t)t;
-                r[i + 1] = (uint32_t)(t >> 32);
+              for (int hh = 0; hh < 2; hh++) {
+                uint32_t rs[32];
+                ptx::tmem_ld32(tmem_lane + buf * 256u + 128u + h * 64 + hh * 32, rs);
+                ptx::tmem_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; i += 2) {
+                  const uint64_t t = ptx::add_f32x2((uint64_t)r[hh * 32 + i] | ((uint64_t)r[hh * 32 + i + 1] << 32), (uint64_t)rs[i] | ((uint64_t)rs[i + 1] << 32));
+                  r[hh * 32 + i] = (uint32_t)t;
+                  r[hh * 32 + i + 1] = (uint32_t)(t >> 32);
+                }
               }
             } else {
               ptx::tmem_wait_ld();
@@ -1012,7 +1025,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
               if (wait_free) rf_ph ^= 1u;
               return;
             }
-            const int col0 = j * X3_NCHUNK + half * 128 + h * 64;
             const uint32_t dst_hi = sA + (uint32_t)(R * X3_RANGE + h * X3_TILE) + row_off;
             uint32_t ph[32], pl[32];
 #pragma unroll
@@ -1028,14 +1040,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                   v[2 * f + 1] = tc::leaky(fmaf(__uint_as_float(r[gq * 8 + 2 * f + 1]), inv, s1), slope);
                 }
               } else {
-                const float4 b0 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8);
-                const float4 b1 = *reinterpret_cast<const float4*>(bias + col0 + gq * 8 + 4);
-                const uint64_t bb[4] = {ptx::pack_f32x2(b0.x, b0.y), ptx::pack_f32x2(b0.z, b0.w),
-                                        ptx::pack_f32x2(b1.x, b1.y), ptx::pack_f32x2(b1.z, b1.w)};
+                uint32_t bw[8];
+                if (gq < 4) {
+#pragma unroll
+                  for (int i = 0; i < 8; i++) bw[i] = bpre[gq * 8 + i];
+                } else {  // 128-bit broadcast loads
+                  ptx::ld_shared_v4u(bias_s + (uint32_t)((col0 + gq * 8) * 4), bw[0], bw[1], bw[2], bw[3]);
+                  ptx::ld_shared_v4u(bias_s + (uint32_t)((col0 + gq * 8 + 4) * 4), bw[4], bw[5], bw[6], bw[7]);
+                }
 #pragma unroll
                 for (int f = 0; f < 4; f++) {
                   const uint64_t acc = (uint64_t)r[gq * 8 + 2 * f] | ((uint64_t)r[gq * 8 + 2 * f + 1] << 32);
-                  const uint64_t t = ptx::fma_f32x2(acc, inv2, bb[f]);
+                  const uint64_t t = ptx::fma_f32x2(acc, inv2, (uint64_t)bw[2 * f] | ((uint64_t)bw[2 * f + 1] << 32));
                   const uint64_t u = ptx::mul_f32x2(t, slope2);
                   v[2 * f] = fmaxf(ptx::f32x2_lo(t), ptx::f32x2_lo(u));
                   v[2 * f + 1] = fmaxf(ptx::f32x2_hi(t), ptx::f32x2_hi(u));
@@ -1048,15 +1064,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                 atomicAdd(reinterpret_cast<double*>(P.prof) + net * 16 + l, (double)cs);
                 atomicAdd(reinterpret_cast<double*>(P.prof) + 32 + net * 16 + l, (double)cw);
               }
+              // a_hi = the value with its mantissa cut to 10 bits (exactly an IEEE half for |v| >= 2^-14), a_lo = the
+              // exact remainder rounded to half: 21 significant bits, one mask + one subtract per value
 #pragma unroll
               for (int f = 0; f < 4; f++) {
-                ph[gq * 4 + f] = ptx::pack_f16x2(v[2 * f], v[2 * f + 1]);
-                const float2 back = ptx::f16x2_to_float2(ph[gq * 4 + f]);
-                pl[gq * 4 + f] = ptx::pack_f16x2(v[2 * f] - back.x, v[2 * f + 1] - back.y);
+                const float h0 = __uint_as_float(__float_as_uint(v[2 * f]) & 0xFFFFE000u);
+                const float h1 = __uint_as_float(__float_as_uint(v[2 * f + 1]) & 0xFFFFE000u);
+                ph[gq * 4 + f] = ptx::pack_f16x2(h0, h1);
+                pl[gq * 4 + f] = ptx::pack_f16x2(v[2 * f] - h0, v[2 * f + 1] - h1);
               }
             }
             if (wait_free) {  // the MMAs of chunk 1 that still read the old K range R
-              ptx::mbar_wait(R_FREE, rf_ph, P.err, 0x680 | l);
+              { const long long t = tick(); ptx::mbar_wait(R_FREE, rf_ph, P.err, 0x680 | l); w1 += tick() - t; }
               rf_ph ^= 1u;
             }
 #pragma unroll
@@ -1084,6 +1103,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       }
       if (half == 0 && h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
     }
+    // counters of warp 2 (lanes [64,96): waits R_FREE(1)) and of warp 4 (lanes [0,32): waits R_FREE(0))
+    if (prof && warp == 2 && lane == 0) { pc[4] = tick() - t_begin; pc[5] = w0; pc[6] = w1; pc[8] = w3; }
+    if (prof && warp == 4 && lane == 0) { pc[7] = w1; pc[13] = w0; }
   }
 
   ptx::tc_fence_before();

@@ -11,10 +11,12 @@ sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 
 
+# the dj_debug_* entry points live in the diagnostics build only (python -m deepjoin_b200.build --debug)
+os.environ.setdefault("DEEPJOIN_B200_LIB", os.path.join(ROOT, "deepjoin_b200", "lib", "libdeepjoin_b200_debug.so"))
+
+
 def bf16_round(a):
-    # the dj_debug_* entry points live in the diagnostics build only (python -m deepjoin_b200.build --debug)
-os.environ.setdefault("DEEPJOIN_B200_LIB", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "deepjoin_b200", "lib", "libdeepjoin_b200_debug.so"))
-import numpy as np
+    import numpy as np
     u = a.astype(np.float32).view(np.uint32).astype(np.uint64)
     u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
     return u.astype(np.uint32).view(np.float32)
@@ -234,7 +236,7 @@ def stage_prof():
     dbg = int(os.environ.get("DEEPJOIN_B200_DEBUG", "0")) | 8
     os.environ["DEEPJOIN_B200_DEBUG"] = str(dbg)
     d = int(os.environ.get("PROF_DIMS", "256"))
-    dec = util.make_decoder(0, "trained_norm", precision="bf16")
+    dec = util.make_decoder(0, "trained_norm", precision=os.environ.get("PROF_PREC", "bf16"))
     code = util.trained_code(0)
     for _ in range(2):
         R.decode_shape_device(code, dec, (d, d, d), use_net=1, padding=0.1, sigmoid=False)
@@ -249,7 +251,8 @@ def stage_prof():
     buf = np.zeros((nsm, 16), np.uint64)
     _lib.check(_lib.lib().dj_debug_read_prof(pack.handle, buf.ctypes.data, buf.size))
     names = ["mma_total", "mma_wait_acc_empty", "mma_wait_a_ready", "mma_wait_w_full", "epi_total", "epi_wait_acc_full",
-             "epi_wait_bar", "epi_l0", "epi_wait_head", "prod_total", "prod_wait_w_empty", "relay_total", "relay_wait"]
+             "epi_wait_bar", "epi_l0", "epi_wait_head", "prod_total", "prod_wait_w_empty", "relay_total", "relay_wait", "epi_w4_wait_acc_full"]
+    # three-pass fp16x2 program: epi_wait_bar = R_FREE(1) wait of warp 2, epi_l0 = R_FREE(0) wait of warp 4
     lead, peer = buf[0::2].astype(np.float64), buf[1::2].astype(np.float64)
     out = {"ms": e0.elapsed_time(e1), "debug": dbg}
     for i, nm in enumerate(names):
