@@ -124,8 +124,11 @@ __device__ __forceinline__ void grid_point(const Params& P, int64_t r, float& x,
 // DBG = 1 compiles the bench diagnostics in (Params::debug knobs and cycle counters); the product path
 // launches DBG = 0.
 // F16 = 1: IEEE-half operands (DJ_PREC_FP16) instead of bf16 -- same instruction, same speed, 8x finer rounding.
-// X2 = 1 (with F16 = 1): split-operand mode, DJ_PREC_FP16X2.  Every activation a and weight W is carried as a
-// high + low IEEE-half pair (22 significant bits) and ALL FOUR partial products are accumulated in fp32:
+// X2 = 2 (with F16 = 1): the three-pass split-operand program, what DJ_PREC_FP16X2 launches -- described where its
+// issuer and its drain are (128 x 256 x 16 MMAs over separate 64-row a_hi / a_lo tiles, two accumulators per chunk).
+// X2 = 1 (with F16 = 1): the four-pass split-operand program (DEEPJOIN_B200_X2_FOURPASS=1; the scheme the latent
+// step uses).  Every activation a and weight W is carried as a high + low IEEE-half pair (22 significant bits) and
+// ALL FOUR partial products are accumulated in fp32:
 //   * a CTA owns 64 points; row m < 64 of its A operand holds a_hi of point m, row m + 64 holds a_lo of the same
 //     point, so one 256 x 128 x 16 MMA of the pair multiplies both halves with a weight tile;
 //   * the weight stream carries the K = 128 stages of a chunk twice, all of W_lo and then all of W_hi (scaled by a

@@ -41,9 +41,10 @@ extern "C" {
 #define DJ_PREC_FP16 2   /* IEEE-half operands on the same kernels (forward only): same speed, 8x finer
                             operand rounding than bf16; the latent step treats it as DJ_PREC_BF16  */
 #define DJ_PREC_FP16X2 3 /* split operands on the tensor cores: activations and weights as high + low IEEE-half
-                            pairs, all four partial products accumulated in fp32 (4x the MMA work per point).
-                            The parity mode: ~1e-5 of the fp64 decoder on trained-norm weights, where single-pass
-                            bf16 / half are at 5e-2 / 8e-3 (forward entry points; latent step: forward half) */
+                            pairs, a_hi.W_hi + a_hi.W_lo + a_lo.W_hi accumulated in fp32 (3x the MMA work per
+                            point in the forward entry points, 4x in the latent step).  The parity mode: ~1e-5 of
+                            the fp64 decoder on trained-norm weights, where single-pass bf16 / half are at
+                            5e-2 / 8e-3 */
 
 /* use_net selector of Decoder.forward (networks/decoder_z_lb_both_leaky_n_sdf.py:345-453) */
 #define DJ_NET_C 0
