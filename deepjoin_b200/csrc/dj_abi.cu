@@ -64,6 +64,7 @@ struct DjPack {
   tc2::Net nets2x[2];
   uint8_t* stream3x[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // three-pass split-operand program
   tc2::Net nets3x[2];
+  bool x3_ok = true;  // false: a layer shape the three-pass program does not cover; DJ_PREC_FP16X2 then runs the four-pass one
   unsigned long long* prof = nullptr;  // [num_sms][16] debug cycle counters (dj_debug_read_prof)
   // fused forward+backward program of the latent step (latent_tc2.cuh)
   uint8_t* lat_stream[2] = {nullptr, nullptr};
@@ -532,11 +533,11 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
       const int k_real = reinj ? K3 : ins[l];
       const float sc = 1.f / T.inv_scale;
       const int k_ranges = T.k_ranges;
-      if (k_ranges > 4) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K=%d exceeds 512 (three-pass program)", l, k_real));
+      if (k_ranges > 4) p->x3_ok = false;
       T.mma_n = (int16_t)(head ? 32 : 256);
       T.n_chunks = (int16_t)(head ? 1 : (n_real + 255) / 256);
-      if (T.n_chunks > 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: width %d exceeds 512 (three-pass program)", l, n_real));
-      if (T.n_chunks > 1 && k_ranges < 2) return bail(fail(DJ_ERR_UNSUPPORTED, "layer %d: K=%d below 129 (three-pass program)", l, k_real));
+      if (T.n_chunks > 2 || (T.n_chunks > 1 && k_ranges < 2)) p->x3_ok = false;
+      if (!p->x3_ok) break;
       T.k_steps = 4;
       T.k_stages = (int16_t)(4 * k_ranges);
       const int rows = T.mma_n / 2;
@@ -563,6 +564,7 @@ extern "C" int dj_pack_create(const DjNetDesc* d, const float* const* f_w, const
                 pack_tile_x2(W[l], ins[l], n_real, k_real, j * T.mma_n + c * rows, r * 128 + kc * 64, rows, blob[c].data() + o, sc, part);
               }
     }
+    if (!p->x3_ok) break;
     for (int r = 0; r < 2; r++) {
       DJ_TRY(cudaMalloc((void**)&p->stream3x[net][r], blob[r].size()));
       DJ_TRY(cudaMemcpy(p->stream3x[net][r], blob[r].data(), blob[r].size(), cudaMemcpyHostToDevice));
@@ -834,7 +836,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
 #else
     static const bool four_pass = getenv("DEEPJOIN_B200_X2_FOURPASS") != nullptr;
 #endif
-    const bool x3 = x2 && !four_pass;
+    const bool x3 = x2 && !four_pass && p->x3_ok;
     P.nets[0] = x3 ? p->nets3x[0] : (x2 ? p->nets2x[0] : p->nets2[0]);
     P.nets[1] = x3 ? p->nets3x[1] : (x2 ? p->nets2x[1] : p->nets2[1]);
     if (f16)

@@ -339,3 +339,28 @@ def test_grid_mode_equals_point_mode_for_any_dims_rows_and_branch():
         assert a.shape == b.shape and torch.equal(a, b)
 
     run()
+
+
+def test_four_pass_program_agrees_with_three_pass(tmp_path):
+    """DJ_PREC_FP16X2 launches the three-pass program; the four-pass one (DEEPJOIN_B200_X2_FOURPASS=1, read once per
+    process, and the fallback for layer shapes the three-pass builder does not cover) must give the same field: both
+    within 1e-4 of the fp64 oracle, within 6e-5 of each other."""
+    import subprocess
+    import sys
+    out_file = str(tmp_path / "four.npy")
+    prog = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
+            "from oracle import synth\nfrom tests import util\n"
+            "dec = util.make_decoder(0, 'trained_norm', precision='fp16x2')\n"
+            "out = dec.query(util.trained_code(0).cuda(), synth.make_points(5000, 4).cuda(), use_net=1)\n"
+            "np.save(%r, out.cpu().numpy())\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), out_file)
+    env = dict(os.environ, DEEPJOIN_B200_X2_FOURPASS="1")
+    subprocess.run([sys.executable, "-c", prog], check=True, env=env, timeout=300)
+    four = np.load(out_file).astype(np.float64)
+    dec = util.make_decoder(0, "trained_norm", precision="fp16x2")
+    pts = synth.make_points(5000, 4)
+    three = dec.query(util.trained_code(0).cuda(), pts.cuda(), use_net=1).cpu().numpy().astype(np.float64)
+    ref = O.forward(util.oracle_net(0, "trained_norm", "float64"), util.trained_code(0).double(), pts.double(), 1).numpy()
+    assert np.abs(three - ref).max() <= 1e-4
+    assert np.abs(four - ref).max() <= 1e-4
+    assert np.abs(three - four).max() <= 6e-5
+    assert not np.array_equal(three, four)  # the environment switch did select another program
