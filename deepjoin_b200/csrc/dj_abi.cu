@@ -818,6 +818,12 @@ static int fp32_forward(DjPack* p, const float* xyz, int64_t n, int net_mask, fl
   return DJ_OK;
 }
 
+// epilogue warps of the three-pass split-operand forward (mlp_tc2.cuh)
+#ifndef DJ_X3_EW
+#define DJ_X3_EW 16
+#endif
+static constexpr int X3_EW = DJ_X3_EW;
+
 // do_fold = false: the caller already folded this code into the pack's tables (several launches with one code)
 static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, const GridSpec& G, int64_t n,
                        const HeadCfg& head, int net_mask, int precision, float* out_dev, cudaStream_t st, bool do_fold = true) {
@@ -868,7 +874,7 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
 #endif
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<0, 1, 2, X3_EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
       p->tc_attr_set2 = true;
     }
 #ifdef DJ_DEBUG
@@ -878,11 +884,11 @@ static int run_forward(DjPack* p, const float* code_dev, const float* xyz_dev, c
       tc2::tc2_forward_kernel<1, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     } else
     if (x3 && P.debug) {
-      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
-      tc2::tc2_forward_kernel<1, 1, 2><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+      DJ_CUDA(cudaFuncSetAttribute(tc2::tc2_forward_kernel<1, 1, 2, X3_EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc2::SMEM_BYTES));
+      tc2::tc2_forward_kernel<1, 1, 2, X3_EW><<<grid, 64 + 32 * X3_EW, tc2::SMEM_BYTES, st>>>(P);
     } else
 #endif
-    if (x3) tc2::tc2_forward_kernel<0, 1, 2><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
+    if (x3) tc2::tc2_forward_kernel<0, 1, 2, X3_EW><<<grid, 64 + 32 * X3_EW, tc2::SMEM_BYTES, st>>>(P);
     else if (x2) tc2::tc2_forward_kernel<0, 1, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
     else if (f16) tc2::tc2_forward_kernel<0, 1><<<grid, tc2::NTHREADS, tc2::SMEM_BYTES, st>>>(P);
 #ifdef DJ_DEBUG

@@ -146,8 +146,11 @@ __device__ __forceinline__ void grid_point(const Params& P, int64_t r, float& x,
 // skipped: both halves of a point ride in the same MMA), error ~1e-5 of fp64 on trained-norm weights, where single
 // pass bf16 has 5e-2 and IEEE half 8e-3.  A 3-pass K-stacked variant would need a_hi and a_lo of 128 points per CTA
 // on chip (2 x 128 KB per buffer, x2 for the ping-pong): it does not fit next to the accumulators.
-template <int DBG, int F16, int X2 = 0>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_forward_kernel(const __grid_constant__ Params P) {
+// EW: epilogue warps (8; the three-pass program also runs with 16: two warps per scheduler cannot hide the latencies
+// of its drain -- TMEM loads, bias loads and stores that queue behind the tensor core's operand reads)
+template <int DBG, int F16, int X2 = 0, int EW = 8>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1) tc2_forward_kernel(const __grid_constant__ Params P) {
+  static_assert(EW == 8 || (EW == 16 && X2 == 2), "16 epilogue warps: three-pass program only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -190,14 +193,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
       // A_READY(0, r): K range r of the next layer's operand is written (4 warps per CTA own a range);
       // A_READY(1, r), r = 0, 1 = "R_FREE(r)": the last MMAs that read K range r of the current layer's operand are
       // done (tcgen05.commit), the drain of chunk 0 may overwrite it
-      for (int c = 0; c < 4; c++) ptx::mbar_init(A_READY(0, c), EPI_WARPS);
+      for (int c = 0; c < 4; c++) ptx::mbar_init(A_READY(0, c), EW);
       for (int c = 0; c < 2; c++) ptx::mbar_init(A_READY(1, c), 1);
     } else {
       for (int c = 0; c < 8; c++) ptx::mbar_init(A_READY(0, c), 2 * EPI_WARPS);
     }
     for (int i = 0; i < 2; i++) {
       ptx::mbar_init(ACC_FULL(i), 1);
-      ptx::mbar_init(ACC_EMPTY(i), 2 * EPI_WARPS);
+      ptx::mbar_init(ACC_EMPTY(i), 2 * EW);
     }
     ptx::mbar_fence_init();
   }
@@ -885,8 +888,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
     // the shared-memory tiles of K range R = 2 j + (q >> 1), k-chunk h of the next layer's operand.  Ranges 0 and 1
     // (drain of chunk 0) are still being read by this layer's chunk 1: their stores wait for R_FREE(R); ranges 2 and
     // 3 are written by the layer's last drain, when nothing reads the old ones any more.
+    // With EW = 16 four warps share a lane quarter and take 32 columns each (hq = 0..3) instead of 64 (hq = h = 0, 1).
+    constexpr int NQ = EW / 4;        // warps per TMEM lane quarter
+    constexpr int CW = 128 / NQ;      // accumulator columns per warp
+    constexpr int NG = CW / 8;        // 8-column (16-byte) groups per warp
+    constexpr int NEPI_T = 32 * EW;   // epilogue threads
+    auto epi_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(NEPI_T) : "memory"); };
     const int q = warp & 3;
-    const int h = (warp - 2) >> 2;
+    const int hq = (warp - 2) >> 2;            // which CW columns of the quarter's 128
+    const int h = (hq * CW) >> 6;              // k-chunk of the next layer's K range
+    const int g0 = ((hq * CW) & 63) >> 3;      // first 16-byte group inside that k-chunk's 128-byte rows
     const int half = q >> 1;
     const int prow = (q & 1) * 32 + lane;  // point of the tile, 0..63
     const int et = threadIdx.x - 64;
@@ -916,13 +927,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
         const Net& N = P.nets[net];
         // ---- layer 0: K = 16 operand [p_hi | p_lo | p_hi | 0] in the first 32 B of the point's a_hi row of K range 0
         // (buffer 0); the tiles hold [W_hi | W_hi | W_lo]
-        tc::epi_bar();  // everybody is past the previous use of sBias
+        epi_bar();  // everybody is past the previous use of sBias
         {
           const float4* t = P.tables + N.l0_table * 512;
-          reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = make_float2(__ldg(&t[2 * et].w), __ldg(&t[2 * et + 1].w));
+          for (int i = et; i < 512; i += NEPI_T) sBias[bias_buf * 512 + i] = __ldg(&t[i].w);
         }
         if (half == 0) {
-          if (h == 0) {
+          if (hq == 0) {
             float hi[3], lo[3];
             const float p3[3] = {x, y, z};
 #pragma unroll
@@ -952,7 +963,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             acc_it++;
             ptx::tc_fence_after();
             uint32_t r[8], rs[8];
-            if (half == 0 && h == 0) {
+            if (half == 0 && hq == 0) {
               ptx::tmem_ld8(tmem_lane + buf * 256u, r);
               ptx::tmem_ld8(tmem_lane + buf * 256u + 128u, rs);
               ptx::tmem_wait_ld();
@@ -960,7 +971,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(lead_accempty0 + 8u * buf);
-            if (half == 0 && h == 0) {
+            if (half == 0 && hq == 0) {
               float* dst = net == 0 ? yc : yt;
 #pragma unroll
               for (int i = 0; i < 5; i++) {
@@ -970,17 +981,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
             }
             continue;
           }
-          tc::epi_bar();
+          epi_bar();
           const int next_kind = (l + 1 < N.n_layers) ? N.layers[l + 1].kind : -1;
           const int next_kr = (l + 1 < N.n_layers) ? N.layers[l + 1].k_ranges : 0;
-          float2 pre_b = make_float2(0.f, 0.f);
-          float4 pre_t0 = make_float4(0, 0, 0, 0), pre_t1 = pre_t0;
+          constexpr int PER = 512 / NEPI_T;  // table entries per thread: 2 or 1
+          float pre_b[PER];
+          float4 pre_t[PER];
           if (next_kind == KIND_HIDDEN) {
-            pre_b = __ldg(reinterpret_cast<const float2*>(P.bias + N.layers[l + 1].bias_off) + et);
+#pragma unroll
+            for (int i = 0; i < PER; i++) pre_b[i] = __ldg(P.bias + N.layers[l + 1].bias_off + et + i * NEPI_T);
           } else if (next_kind == KIND_HIDDEN_XYZ) {
             const float4* t = P.tables + N.layers[l + 1].table * 512;
-            pre_t0 = __ldg(t + et);
-            pre_t1 = __ldg(t + et + 256);
+#pragma unroll
+            for (int i = 0; i < PER; i++) pre_t[i] = __ldg(t + et + i * NEPI_T);
           }
           const uint32_t bias_s = base + SM_BIAS + (uint32_t)(bias_buf * 2048);
           const uint64_t inv2 = ptx::pack_f32x2(inv, inv);
@@ -988,32 +1001,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
           auto drain = [&](auto kind_c, int j) {
             constexpr int KIND = decltype(kind_c)::value;
             const uint32_t buf = acc_it & 1u;
-            const int col0 = j * X3_NCHUNK + half * 128 + h * 64;
+            const int col0 = j * X3_NCHUNK + half * 128 + hq * CW;
             // the first half of this warp's bias values is fetched while the accumulator is still being computed: the
             // tensor core's operand reads keep the shared-memory pipe busy, a load issued inside the drain waits long
-            uint32_t bpre[32];
+            uint32_t bpre[CW / 2];
             if (KIND != KIND_HIDDEN_XYZ) {
 #pragma unroll
-              for (int i = 0; i < 8; i++)
+              for (int i = 0; i < CW / 8; i++)
                 ptx::ld_shared_v4u(bias_s + (uint32_t)((col0 + 4 * i) * 4), bpre[4 * i], bpre[4 * i + 1], bpre[4 * i + 2], bpre[4 * i + 3]);
             }
             { const long long t = tick(); ptx::mbar_wait(ACC_FULL(buf), (acc_it >> 1) & 1u, P.err, 0x600 | j); w0 += tick() - t; }
             acc_it++;
             ptx::tc_fence_after();
-            uint32_t r[64];
-            ptx::tmem_ld64(tmem_lane + buf * 256u + h * 64, r);
+            uint32_t r[CW];
+            ptx::tmem_ld_n<CW>(tmem_lane + buf * 256u + hq * CW, r);
             if (L.k_steps != 1) {  // + the accumulator of the small products (layer 0 is a single MMA); in two halves:
-              // 64 + 64 live accumulator registers do not fit next to the rest (168 registers per thread)
+              // CW + CW live accumulator registers do not fit next to the rest
 #pragma unroll
               for (int hh = 0; hh < 2; hh++) {
-                uint32_t rs[32];
-                ptx::tmem_ld32(tmem_lane + buf * 256u + 128u + h * 64 + hh * 32, rs);
+                uint32_t rs[CW / 2];
+                ptx::tmem_ld_n<CW / 2>(tmem_lane + buf * 256u + 128u + hq * CW + hh * (CW / 2), rs);
                 ptx::tmem_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; i += 2) {
-                  const uint64_t t = ptx::add_f32x2((uint64_t)r[hh * 32 + i] | ((uint64_t)r[hh * 32 + i + 1] << 32), (uint64_t)rs[i] | ((uint64_t)rs[i + 1] << 32));
-                  r[hh * 32 + i] = (uint32_t)t;
-                  r[hh * 32 + i + 1] = (uint32_t)(t >> 32);
+                for (int i = 0; i < CW / 2; i += 2) {
+                  const uint64_t t = ptx::add_f32x2((uint64_t)r[hh * (CW / 2) + i] | ((uint64_t)r[hh * (CW / 2) + i + 1] << 32),
+                                                    (uint64_t)rs[i] | ((uint64_t)rs[i + 1] << 32));
+                  r[hh * (CW / 2) + i] = (uint32_t)t;
+                  r[hh * (CW / 2) + i + 1] = (uint32_t)(t >> 32);
                 }
               }
             } else {
@@ -1029,9 +1043,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
               return;
             }
             const uint32_t dst_hi = sA + (uint32_t)(R * X3_RANGE + h * X3_TILE) + row_off;
-            uint32_t ph[32], pl[32];
+            uint32_t ph[CW / 2], pl[CW / 2];
 #pragma unroll
-            for (int gq = 0; gq < 8; gq++) {
+            for (int gq = 0; gq < NG; gq++) {
               float v[8];
               if (KIND == KIND_HIDDEN_XYZ) {
 #pragma unroll
@@ -1044,7 +1058,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
                 }
               } else {
                 uint32_t bw[8];
-                if (gq < 4) {
+                if (gq < NG / 2) {
 #pragma unroll
                   for (int i = 0; i < 8; i++) bw[i] = bpre[gq * 8 + i];
                 } else {  // 128-bit broadcast loads
@@ -1082,8 +1096,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
               rf_ph ^= 1u;
             }
 #pragma unroll
-            for (int gq = 0; gq < 8; gq++) {
-              const uint32_t d = dst_hi + ((gq ^ sw) << 4);
+            for (int gq = 0; gq < NG; gq++) {
+              const uint32_t d = dst_hi + (((g0 + gq) ^ sw) << 4);
               tc::st_shared_v4(d, ph[gq * 4], ph[gq * 4 + 1], ph[gq * 4 + 2], ph[gq * 4 + 3]);
               tc::st_shared_v4(d + X3_PART, pl[gq * 4], pl[gq * 4 + 1], pl[gq * 4 + 2], pl[gq * 4 + 3]);
             }
@@ -1097,14 +1111,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1) tc2_for
           else for (int j = 0; j < L.n_chunks; j++) drain(I0{}, j);
           if (next_kind == KIND_HIDDEN) {
             bias_buf ^= 1;
-            reinterpret_cast<float2*>(sBias + bias_buf * 512)[et] = pre_b;
+#pragma unroll
+            for (int i = 0; i < PER; i++) sBias[bias_buf * 512 + et + i * NEPI_T] = pre_b[i];
           } else if (next_kind == KIND_HIDDEN_XYZ) {
-            sTab[et] = pre_t0;
-            sTab[et + 256] = pre_t1;
+#pragma unroll
+            for (int i = 0; i < PER; i++) sTab[et + i * NEPI_T] = pre_t[i];
           }
         }
       }
-      if (half == 0 && h == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
+      if (half == 0 && hq == 0 && g < P.n) write_heads(P.head, yc, yt, P.out, g);
     }
     // counters of warp 2 (lanes [64,96): waits R_FREE(1)) and of warp 4 (lanes [0,32): waits R_FREE(0))
     if (prof && warp == 2 && lane == 0) { pc[4] = tick() - t_begin; pc[5] = w0; pc[6] = w1; pc[8] = w3; }
