@@ -347,6 +347,8 @@ def test_four_pass_program_agrees_with_three_pass(tmp_path):
     within 1e-4 of the fp64 oracle, within 6e-5 of each other."""
     import subprocess
     import sys
+    if os.environ.get("DEEPJOIN_B200_X2_FOURPASS"):
+        pytest.skip("this process already runs the four-pass program")
     out_file = str(tmp_path / "four.npy")
     prog = ("import sys, numpy as np, torch; sys.path.insert(0, %r)\n"
             "from oracle import synth\nfrom tests import util\n"
