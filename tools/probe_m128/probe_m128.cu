@@ -111,6 +111,60 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) probe_kernel
   if (warp == 0) ptx::tmem_dealloc2(tmem, 512);
 }
 
+
+// (5) can a 1-D bulk copy into THIS CTA's shared memory signal the mbarrier of the OTHER CTA of the pair?  Both CTAs copy
+// `bytes` into their own shared memory; mode 0: each signals its own barrier and CTA 1 relays with a remote arrive (what
+// the decoder kernels do), mode 1: both signal CTA 0's barrier directly.  CTA 0 measures issue -> completion.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64, 1) relay_kernel(const uint8_t* src, uint32_t bytes, int mode, int reps,
+                                                                                 long long* cycles, uint32_t* sums, unsigned int* err) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - ptx::smem_u32(smem_raw));
+  const uint32_t bar = base + 32768, go = bar + 8;
+  const uint32_t rank = ptx::cluster_ctarank();
+  if (threadIdx.x == 0) {
+    ptx::mbar_init(bar, mode == 0 ? (rank == 0 ? 2 : 1) : 1);
+    ptx::mbar_init(go, 1);
+    ptx::mbar_fence_init();
+  }
+  __syncthreads();
+  ptx::cluster_sync();
+  const uint32_t lead_bar = ptx::mapa(bar, 0), peer_go = ptx::mapa(go, 1);
+  long long total = 0;
+  for (int r = 0; r < reps; r++) {
+    const uint32_t ph = (uint32_t)(r & 1);
+    if (rank == 0 && threadIdx.x == 0) {
+      const long long t0 = clock64();
+      ptx::mbar_arrive_cluster(peer_go);  // tell the peer to start its copy now
+      if (mode == 0) ptx::mbar_expect_tx(bar, bytes);
+      else ptx::mbar_expect_tx(bar, 2 * bytes);
+      ptx::bulk_g2s(base, src, bytes, mode == 0 ? bar : lead_bar);
+      ptx::mbar_wait(bar, ph, err, 0x901);
+      total += clock64() - t0;
+    }
+    if (rank == 1 && threadIdx.x == 0) {
+      ptx::mbar_wait(go, ph, err, 0x902);
+      if (mode == 0) {
+        ptx::mbar_expect_tx(bar, bytes);
+        ptx::bulk_g2s(base, src + bytes, bytes, bar);
+      } else {
+        ptx::bulk_g2s(base, src + bytes, bytes, lead_bar);
+      }
+    }
+    if (rank == 1 && threadIdx.x == 32 && mode == 0) {  // relay warp
+      ptx::mbar_spin(bar, ph);
+      ptx::mbar_arrive_cluster(lead_bar);
+    }
+    __syncthreads();
+    ptx::cluster_sync();
+  }
+  // checksum of what landed
+  uint32_t s = 0;
+  for (uint32_t i = threadIdx.x; i < bytes / 4; i += 64) s += reinterpret_cast<const uint32_t*>(smem)[i];
+  atomicAdd(&sums[rank], s);
+  if (rank == 0 && threadIdx.x == 0) cycles[0] = total;
+}
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 struct Run {
@@ -225,6 +279,30 @@ int main(int argc, char** argv) {
       printf("timing cta_group::2 M=%d N=%d K=16 %s%s: %lld cycles for %d MMAs = %.1f cycles/MMA, %.0f MAC/cycle/SM\n", M, N, a_tmem ? "TS" : "SS",
              alt ? ", two accumulators alternating every 4 MMAs" : "", R.cycles, reps * 4, (double)R.cycles / (reps * 4),
              (double)M * N * 16 / 2 / ((double)R.cycles / (reps * 4)));
+    }
+  }
+
+  if (section == 5) {
+    const uint32_t bytes = 16384;
+    std::vector<uint32_t> h(2 * bytes / 4);
+    uint32_t want[2] = {0, 0};
+    for (size_t i = 0; i < h.size(); i++) { h[i] = (uint32_t)(i * 2654435761u + 12345u); want[i / (bytes / 4)] += h[i]; }
+    uint8_t* d; long long* dC; uint32_t* dS; unsigned int* dE;
+    CK(cudaMalloc(&d, 2 * bytes)); CK(cudaMalloc(&dC, 8)); CK(cudaMalloc(&dS, 8)); CK(cudaMalloc(&dE, 4));
+    CK(cudaMemcpy(d, h.data(), 2 * bytes, cudaMemcpyHostToDevice));
+    const int smem = 32768 + 64 + 1024;
+    CK(cudaFuncSetAttribute(relay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    for (int mode = 0; mode < 2; mode++) {
+      const int reps = 200;
+      CK(cudaMemset(dS, 0, 8)); CK(cudaMemset(dE, 0, 4)); CK(cudaMemset(dC, 0, 8));
+      relay_kernel<<<2, 64, smem>>>(d, bytes, mode, reps, dC, dS, dE);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mode %d: launch failed: %s\n", mode, cudaGetErrorString(e)); break; }
+      long long c; uint32_t sgot[2]; unsigned int eh;
+      CK(cudaMemcpy(&c, dC, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(sgot, dS, 8, cudaMemcpyDeviceToHost)); CK(cudaMemcpy(&eh, dE, 4, cudaMemcpyDeviceToHost));
+      printf("bulk copy completion %s: %.0f cycles from issue to the leader seeing both halves (16 KB each, L2 hits); data %s; watchdog 0x%x\n",
+             mode == 0 ? "on own barriers + remote arrive relay" : "signalled on the leader's barrier by both CTAs", (double)c / reps,
+             (sgot[0] == want[0] && sgot[1] == want[1]) ? "OK" : "WRONG", eh);
     }
   }
   return 0;
