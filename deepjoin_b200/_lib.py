@@ -14,7 +14,7 @@ LIB_PATH = os.environ.get("DEEPJOIN_B200_LIB") or os.path.join(_HERE, "lib", "li
 (OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_NO_SURFACE, ERR_LEVEL_RANGE, ERR_NO_SAMPLES, ERR_BAD_NET, ERR_DEVICE,
  ERR_PERMISSION, ERR_IO) = range(11)
 PREC = {"fp32": 0, "bf16": 1, "fp16": 2, "fp16x2": 3}
-ABI_VERSION = 3  # == DJ_ABI_VERSION in include/deepjoin_b200.h (checked by tests/test_host_cpu.py)
+ABI_VERSION = 4  # == DJ_ABI_VERSION in include/deepjoin_b200.h (checked by tests/test_host_cpu.py)
 
 c_i, c_i64, c_d, c_f, c_p = ctypes.c_int, ctypes.c_int64, ctypes.c_double, ctypes.c_float, ctypes.c_void_p
 
@@ -64,7 +64,7 @@ SIGNATURES = {
     "dj_mesh_merge_vertices": (c_i, [c_p, c_p, c_i64, c_p, c_i64, ctypes.POINTER(c_i64), c_p]),
     "dj_nn_query": (c_i, [c_p, c_i64, c_p, c_i64, c_p, c_p, c_p]),
     "dj_launch_count": (c_i64, [c_i]),
-    "dj_host_sample_schedule": (c_i, [c_p, c_p, c_p, c_i64, ctypes.c_double, c_i, c_i, c_i, c_p]),
+    "dj_host_sample_schedule": (c_i, [c_p, c_p, c_p, c_i64, ctypes.c_double, c_i, c_i, c_i, c_p, c_p]),
 }
 
 # diagnostics that only a -DDJ_DEBUG build exports (python -m deepjoin_b200.build --debug; DEEPJOIN_B200_LIB selects it)

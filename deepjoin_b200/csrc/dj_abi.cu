@@ -34,6 +34,8 @@ struct DjCtx {
   unsigned int* err = nullptr;
   DevBuf ws_fwd, ws_lat, ws_host, ws_mask;
   PinBuf pin_host;  // staging of dj_decode_samples_host
+  std::vector<const float*> lat_ptrs;     // the sample-array pointers last uploaded for the latent step ...
+  const float** lat_ptrs_dev = nullptr;   // ... and where they went (a block-wise loop uploads them once)
   ~DjCtx() {
     if (tables) cudaFree(tables);
     if (err) cudaFree(err);
@@ -1111,6 +1113,7 @@ static int carve_latent(DjPack* p, int64_t n, LatWs& W, cudaStream_t st, bool sm
   const size_t act = small ? 0 : (size_t)n * 512;
   const size_t floats = (size_t)(nf + nh + 2) * act + 4 * (size_t)n * 8 + 3 * 512 + 8 + 256 + 8 + (size_t)n * 7 + 64;
   DJ_CUDA(c->ws_lat.reserve(floats * sizeof(float)));
+  c->lat_ptrs_dev = nullptr;  // this layout overwrites the tensor-core step's pointer table
   float* q = c->ws_lat.as<float>();
   W.fH.resize(nf + 1); W.hH.resize(nh + 1);
   for (int l = 0; l < nf; l++) { W.fH[l] = q; q += act; }
@@ -1201,11 +1204,18 @@ static int carve_latent_tc(DjPack* p, int S, LatTcWs& W, cudaStream_t st) {
   return DJ_OK;
 }
 // upload the per-shape sample array pointers (once per optimisation, not per iteration)
-static int upload_ptrs(LatTcWs& W, int S, const float* const* xyz, const float* const* sdf, const float* const* nrm, cudaStream_t st) {
+static int upload_ptrs(DjPack* p, LatTcWs& W, int S, const float* const* xyz, const float* const* sdf, const float* const* nrm, cudaStream_t st) {
+  DJ_CTX(c, p, st);
   std::vector<const float*> h((size_t)3 * S);
   for (int s = 0; s < S; s++) { h[s] = xyz[s]; h[S + s] = sdf[s]; h[2 * S + s] = nrm[s]; }
-  DJ_CUDA(cudaMemcpyAsync(W.ptrs, h.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
-  DJ_CUDA(cudaStreamSynchronize(st));  // h goes out of scope
+  // the next block of a block-wise loop (DjLatentCfg.iter_offset > 0) finds them in place: no copy, and no
+  // synchronisation, so the block is enqueued while the previous one still runs
+  if (c->lat_ptrs_dev == W.ptrs && c->lat_ptrs == h) return DJ_OK;
+  DJ_CUDA(cudaStreamSynchronize(st));  // a loop still reading the old pointers
+  c->lat_ptrs = h;
+  c->lat_ptrs_dev = W.ptrs;
+  DJ_CUDA(cudaMemcpyAsync(W.ptrs, c->lat_ptrs.data(), h.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+  DJ_CUDA(cudaStreamSynchronize(st));
   return DJ_OK;
 }
 
@@ -1286,7 +1296,7 @@ extern "C" int dj_latent_grad(DjPack* p, const float* code_dev, const float* xyz
   if (cfg->precision != DJ_PREC_FP32) {  // tensor cores (bf16 operands; gradients underflow in IEEE half)
     LatTcWs T;
     if ((rc = carve_latent_tc(p, 1, T, st))) return rc;
-    if ((rc = upload_ptrs(T, 1, &xyz_dev, &sdf_dev, &nrm_dev, st))) return rc;
+    if ((rc = upload_ptrs(p, T, 1, &xyz_dev, &sdf_dev, &nrm_dev, st))) return rc;
     if ((rc = latent_fwd_bwd_tc(p, 1, code_dev, nullptr, 0, n, cfg, T, st))) return rc;
     if ((rc = check_err_word(p, st))) return rc;
     DJ_CUDA(cudaMemcpyAsync(grad_dev, T.grad, (p->L + p->Lb) * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -1327,7 +1337,7 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
     // all shapes in one launch per iteration; the kernel gathers every shape's mini-batch rows itself
     LatTcWs T;
     if ((rc = carve_latent_tc(p, n_shapes, T, st))) return rc;
-    if ((rc = upload_ptrs(T, n_shapes, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, st))) return rc;
+    if ((rc = upload_ptrs(p, T, n_shapes, pool_xyz_dev, pool_sdf_dev, pool_nrm_dev, st))) return rc;
     const int64_t idx_stride = (int64_t)cfg->num_iterations * n;
     for (int el = 0; el < cfg->num_iterations; el++) {
       const int e = e0 + el;
@@ -1337,8 +1347,10 @@ extern "C" int dj_latent_optimize_batch(DjPack* p, int n_shapes, float* codes_de
                                                   (long long)log_rows * 8);
       DJ_LAUNCHED();
     }
-    // a device watchdog that fired during the loop must not go unnoticed (this synchronises the stream once per
-    // call; the caller reads the codes right after anyway)
+    // a device watchdog that fired during the loop must not go unnoticed: checked after the LAST block of the loop
+    // (this synchronises the stream; the caller reads the codes right after anyway).  Earlier blocks of a block-wise
+    // loop return as soon as they are enqueued, so that the host can stage the next block meanwhile.
+    if (e0 + cfg->num_iterations < total) return DJ_OK;
     return check_err_word(p, st);
   }
   // fp32 (reference arithmetic): shape after shape

@@ -277,8 +277,10 @@ extern "C" int dj_host_mt19937_permutation(uint32_t* key624, int32_t* pos, int64
 // shape.  So the calling thread walks the stream -- the swap partners of both shuffles, the first shuffle itself,
 // the class counts, the window starts -- and hands everything that is independent from there (second shuffle,
 // locating the windows, writing the rows) to worker threads.
+// progress (optional): *progress = number of LEADING iterations whose rows are final, stored with release order as
+// the workers finish -- a consumer thread can hand rows [0, *progress) to the device while the rest is still drawn.
 extern "C" int dj_host_sample_schedule(uint32_t* key624, int32_t* pos, const float* sdf, int64_t n_pts, double uniform_ratio,
-                                       int num_iterations, int num_samples, int n_threads, int32_t* out) {
+                                       int num_iterations, int num_samples, int n_threads, int32_t* out, int32_t* progress) {
   if (!key624 || !pos || !sdf || !out || n_pts < 2 || num_iterations < 0 || num_samples < 1 || *pos < 0 || *pos > 624)
     return fail(DJ_ERR_INVALID, "dj_host_sample_schedule: bad argument");
   if (n_pts > 0x7fffffffll) return fail(DJ_ERR_UNSUPPORTED, "dj_host_sample_schedule: more than 2^31 - 1 rows");
@@ -308,6 +310,9 @@ extern "C" int dj_host_sample_schedule(uint32_t* key624, int32_t* pos, const flo
   std::condition_variable cv_job, cv_room;
   std::deque<std::unique_ptr<Job>> queue, spare;  // spare: finished jobs whose buffers the next iterations reuse
   bool done = false;
+  std::vector<char> finished((size_t)std::max(num_iterations, 1), 0);
+  int lead = 0;  // iterations [0, lead) are complete (under mu)
+  if (progress) __atomic_store_n(progress, 0, __ATOMIC_RELEASE);
   std::vector<std::thread> workers;
   for (int t = 0; t < nw; t++)
     workers.emplace_back([&] {
@@ -323,6 +328,9 @@ extern "C" int dj_host_sample_schedule(uint32_t* key624, int32_t* pos, const flo
         finish(*J, sdf, num_samples, out + (size_t)J->e * num_samples);
         {
           std::lock_guard<std::mutex> lk(mu);
+          finished[(size_t)J->e] = 1;
+          while (lead < num_iterations && finished[(size_t)lead]) lead++;
+          if (progress) __atomic_store_n(progress, lead, __ATOMIC_RELEASE);
           spare.push_back(std::move(J));
         }
         cv_room.notify_one();

@@ -31,10 +31,13 @@ from deepjoin_b200.core import data as _data
 LOG_KEYS = ("epoch", "loss", "sdf_data_loss", "occ_data_loss", "norm_loss", "reg_loss", "mag", "h_mag")
 
 
-def make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio=0.2):
+def make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio=0.2, n_threads=0, out=None, progress=None):
     """Row indices of every iteration's mini-batch, consuming numpy's global RNG exactly as the
-    reference loop does (reconstruct.py:114-118 -> core/data.py:15-73)."""
-    sched = np.empty((num_iterations, num_samples), dtype=np.int32)
+    reference loop does (reconstruct.py:114-118 -> core/data.py:15-73).  ``n_threads``: worker threads of the native
+    sampler (0 = one per core but one).  ``out`` / ``progress``: a preallocated int32 [num_iterations, num_samples]
+    array and a ctypes.c_int32 the native sampler keeps at the number of finished leading iterations (another
+    thread may consume those rows while the call is still running)."""
+    sched = np.empty((num_iterations, num_samples), dtype=np.int32) if out is None else out
     vals = np.ascontiguousarray(_data._f32(np.asarray(b_sdf_gt).reshape(-1)), dtype=np.float32)  # widened once
     state = np.random.get_state()
     if (state[0] == "MT19937" and uniform_ratio is not None and 0.0 < uniform_ratio < 1.0 and vals.shape[0] >= 2
@@ -45,13 +48,15 @@ def make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio=0.2):
         key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
         pos = ctypes.c_int32(int(state[2]))
         rc = _lib.lib().dj_host_sample_schedule(key.ctypes.data, ctypes.byref(pos), vals.ctypes.data, vals.shape[0],
-                                                float(uniform_ratio), int(num_iterations), int(num_samples), 0,
-                                                sched.ctypes.data)
+                                                float(uniform_ratio), int(num_iterations), int(num_samples), int(n_threads),
+                                                sched.ctypes.data, ctypes.byref(progress) if progress is not None else None)
         np.random.set_state((state[0], key, pos.value, state[3], state[4]))
         _lib.check(rc)
         return sched
     for e in range(num_iterations):
         sched[e] = _data.select_sample_indices(vals, num_samples, uniform_ratio=uniform_ratio)
+        if progress is not None:
+            progress.value = e + 1
     return sched
 
 
@@ -109,10 +114,32 @@ def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, la
     v = torch.zeros_like(code)
     log = torch.zeros(((total + log_every - 1) // log_every, 8), device=dev, dtype=torch.float32)
     done, keep = 0, []
+    side, stage, k = None, [None, None], 0
     for block in schedule_blocks:
         if not isinstance(block, torch.Tensor):
             block = torch.from_numpy(np.ascontiguousarray(block, dtype=np.int32))
-        block = block.to(device=dev, dtype=torch.int32, non_blocking=True).contiguous()
+        if block.device.type == "cpu":
+            # Host blocks go through one of two pinned staging buffers on a side stream: the library enqueues a block
+            # without waiting for the previous one (only the last block synchronises), so this copy overlaps the
+            # running iterations.
+            if side is None:
+                side = torch.cuda.Stream(dev)
+            buf, ev = stage[k & 1] or (None, None)
+            if ev is not None:
+                ev.synchronize()  # the copy that last read this staging buffer
+            if buf is None or buf.numel() < block.numel():
+                buf = torch.empty(block.numel(), dtype=torch.int32, pin_memory=True)
+            pinned = buf[:block.numel()].view(block.shape)
+            pinned.copy_(block)
+            with torch.cuda.stream(side):
+                block = pinned.to(device=dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            stage[k & 1] = (buf, ev)
+            k += 1
+        else:
+            block = block.to(device=dev, dtype=torch.int32).contiguous()
         keep.append(block)  # the enqueued iterations read it
         n_k, ns = int(block.shape[0]), int(block.shape[1])
         cfg = _lib.LatentCfg(n_k, ns, float(lr), float(lambda1), float(lambda3), float(clamp_dist),
@@ -131,35 +158,50 @@ def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, la
     return log, code.reshape(1, -1)
 
 
-def _schedule_blocks(b_sdf_gt, num_iterations, num_samples, uniform_ratio, block=100):
-    """make_schedule in blocks of `block` iterations on a background thread (numpy's global stream, in order): the
-    native sampler releases the GIL, the consumer enqueues block k on the device while block k + 1 is drawn."""
-    import queue
+def _schedule_blocks(b_sdf_gt, num_iterations, num_samples, uniform_ratio, block=100, first=10):
+    """The reference sampler's schedule of a whole reconstruct() call, drawn by ONE make_schedule call on a background
+    thread (numpy's global stream, in order; the native sampler releases the GIL) and handed out while it is being
+    drawn: yields views of the leading finished iterations, `first` iterations as soon as they exist (the device starts
+    after ~15 ms), then whatever has accumulated, at most `block`, in multiples of 10 (the log interval)."""
+    import ctypes
     import threading
-    q = queue.Queue(maxsize=4)
+    import time
+    sched = np.empty((num_iterations, num_samples), dtype=np.int32)
+    progress = ctypes.c_int32(0)
+    failure = []
+    # the thread that walks numpy's generator is the sampler's critical path: leave two cores to the thread that
+    # launches the device work and to the driver
+    workers = max(1, (os.cpu_count() or 4) - 3)
 
     def produce():
         try:
-            e = 0
-            while e < num_iterations:
-                n_k = min(block, num_iterations - e)
-                q.put(make_schedule(b_sdf_gt, n_k, num_samples, uniform_ratio))
-                e += n_k
-            q.put(None)
+            make_schedule(b_sdf_gt, num_iterations, num_samples, uniform_ratio, n_threads=workers, out=sched, progress=progress)
         except BaseException as exc:  # noqa: BLE001 -- re-raised in the consumer (NoSamplesError keeps its type)
-            q.put(exc)
+            failure.append(exc)
 
     t = threading.Thread(target=produce, daemon=True)
     t.start()
-    while True:
-        item = q.get()
-        if item is None:
-            break
-        if isinstance(item, BaseException):
+    emitted, want = 0, max(1, min(first, block))
+    while emitted < num_iterations:
+        alive = t.is_alive()
+        ready = min(int(progress.value), num_iterations)
+        if failure:
             t.join()
-            raise item
-        yield item
+            raise failure[0]
+        if not alive and not failure and ready < num_iterations:
+            ready = num_iterations  # the Python fallback sampler finished without the counter
+        take = min(ready - emitted, block)
+        if ready < num_iterations:
+            take -= take % 10
+        if take >= min(want, num_iterations - emitted) and take > 0:
+            yield sched[emitted:emitted + take]
+            emitted += take
+            want = 10
+        else:
+            time.sleep(0.0005)
     t.join()
+    if failure:
+        raise failure[0]
 
 
 def optimize_codes(decoder, codes0, pools, schedules, lr, lambda1, lambda3, clamp_dist, l2reg=True, code_reg_lambda=1e-4,

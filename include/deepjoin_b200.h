@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DJ_ABI_VERSION 3
+#define DJ_ABI_VERSION 4
 
 /* status codes */
 #define DJ_OK 0
@@ -136,7 +136,9 @@ typedef struct DjLatentCfg {
    * block while the device works on the previous block): this call runs iterations iter_offset ..
    * iter_offset + num_iterations - 1 of a loop of total_iterations (0 = num_iterations) -- lr step, Adam bias
    * correction and log rows follow the GLOBAL iteration; adam_m / adam_v / codes / log carry over between calls,
-   * idx_dev holds this call's num_iterations rows only */
+   * idx_dev holds this call's num_iterations rows only.  With the tensor-core precisions a call that does not reach
+   * total_iterations returns as soon as its iterations are enqueued (idx_dev must stay valid until the stream has
+   * run them); the call that completes the loop synchronises the stream and reports a device fault of any block */
   int32_t iter_offset;
   int32_t total_iterations;
 } DjLatentCfg;
@@ -190,10 +192,11 @@ int dj_host_mt19937_permutation(uint32_t* key624, int32_t* pos, int64_t n, int64
  * numpy's global MT19937 stream: out [num_iterations][num_samples] int32 row indices, bit-identical to calling the
  * reference sampler num_iterations times from the state (key624, *pos) (np.random.get_state()); *pos / key624 are
  * left where numpy would be.  sdf [n_pts] float32 (one value column).  The calling thread walks the generator,
- * n_threads workers (0 = host cores - 1) finish the shuffles.  DJ_ERR_NO_SAMPLES where the reference raises
- * NoSamplesError.  No GPU. */
+ * n_threads workers (0 = host cores - 1) finish the shuffles.  progress (optional): *progress = number of leading
+ * iterations whose rows are final, updated as the call proceeds, so that another thread can consume them meanwhile.
+ * DJ_ERR_NO_SAMPLES where the reference raises NoSamplesError.  No GPU. */
 int dj_host_sample_schedule(uint32_t* key624, int32_t* pos, const float* sdf, int64_t n_pts, double uniform_ratio,
-                            int num_iterations, int num_samples, int n_threads, int32_t* out);
+                            int num_iterations, int num_samples, int n_threads, int32_t* out, int32_t* progress);
 
 /* replaces: core.data.select_samples(pts, values, num_samples, uniform_ratio)
  * (core/data.py:15-73,122-176) for every iteration at once, on the device, from a counter
