@@ -128,7 +128,9 @@ def optimize_code(decoder, code0, pool_xyz, pool_sdf, pool_nrm, schedule, lr, la
             if ev is not None:
                 ev.synchronize()  # the copy that last read this staging buffer
             if buf is None or buf.numel() < block.numel():
-                buf = torch.empty(block.numel(), dtype=torch.int32, pin_memory=True)
+                # sized for the largest block the producer hands out (100 iterations), so that it is allocated once
+                # (torch's pinned pool then serves the same two blocks to every later call)
+                buf = torch.empty(max(block.numel(), 100 * int(block.shape[1])), dtype=torch.int32, pin_memory=True)
             pinned = buf[:block.numel()].view(block.shape)
             pinned.copy_(block)
             with torch.cuda.stream(side):
