@@ -7,9 +7,9 @@ Same arguments, same return value ``(loss_dict, code[1, L+Lb])``, same initialis
 stream (numpy global RNG consumed exactly like core/data.py does), but the 800-iteration loop
 -- batch gather, forward, clamped-L1 + BCE + normal loss, backward to the code only, Adam, lr
 step, loss logging every 10th iteration -- runs on the device without host round trips
-(dj_latent_optimize).  The reference's sampler (62 ms per iteration in numpy) is one native call per block of 100
-iterations on numpy's own MT19937 stream (dj_host_sample_schedule, ~1 ms per iteration, bit-identical rows), drawn on a
-background thread while the device works on the previous block.  ``sampling_method="device"`` (extension) draws
+(dj_latent_optimize).  The reference's sampler (62 ms per iteration in numpy) is ONE native call on numpy's own
+MT19937 stream (dj_host_sample_schedule, ~1 ms per iteration, bit-identical rows) on a background thread; the rows of
+its finished leading iterations go to the device in 10-iteration blocks while the rest is still being drawn.  ``sampling_method="device"`` (extension) draws
 the schedule on the device instead (dj_sample_schedule; same distribution, not numpy's stream).
 
 Arithmetic follows ``decoder.precision`` (override: ``decoder.latent_precision``):
