@@ -175,6 +175,36 @@ def test_native_schedule_matches_the_reference_made_fixture():
         assert np.array_equal(pts[idx], g[key + "_pts"]) and np.array_equal(g["sdf"][idx], g[key + "_vals"])
 
 
+@pytest.mark.parametrize("iters,py_sampler", [(137, False), (6, False), (30, False), (23, True)])
+def test_streamed_schedule_blocks_equal_one_call(iters, py_sampler):
+    """reconstruct()'s producer (_schedule_blocks: one sampler call on a background thread, finished leading
+    iterations handed out through the progress counter) yields exactly make_schedule's rows, in blocks that are
+    multiples of the log interval except the last, and leaves numpy's generator where one call would."""
+    import synth_data
+    from deepjoin_b200 import reconstruct as R
+    sdf = np.ascontiguousarray(synth_data.make_sample_set(60000, seed=5)[1].reshape(-1), dtype=np.float32)
+    if py_sampler:
+        os.environ["DEEPJOIN_B200_PY_SAMPLER"] = "1"
+    try:
+        np.random.seed(9)
+        whole = R.make_schedule(sdf, iters, 4000, 0.2)
+        tail_a = np.random.randint(1 << 30)
+        np.random.seed(9)
+        blocks = [b.copy() for b in R._schedule_blocks(sdf, iters, 4000, 0.2)]
+        tail_b = np.random.randint(1 << 30)
+    finally:
+        os.environ.pop("DEEPJOIN_B200_PY_SAMPLER", None)
+    assert all(b.shape[0] % 10 == 0 for b in blocks[:-1]) and all(0 < b.shape[0] <= 100 for b in blocks)
+    assert np.array_equal(np.concatenate(blocks), whole) and tail_a == tail_b
+
+
+def test_streamed_schedule_blocks_propagate_no_samples_error():
+    from deepjoin_b200 import reconstruct as R
+    from deepjoin_b200.core import errors
+    with pytest.raises(errors.NoSamplesError):
+        list(R._schedule_blocks(np.full(1000, 0.5, np.float32), 20, 100, 0.2))
+
+
 def test_native_schedule_raises_no_samples_error():
     from deepjoin_b200 import reconstruct as R
     from deepjoin_b200.core import errors
