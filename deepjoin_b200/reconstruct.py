@@ -183,25 +183,28 @@ def _schedule_blocks(b_sdf_gt, num_iterations, num_samples, uniform_ratio, block
 
     t = threading.Thread(target=produce, daemon=True)
     t.start()
-    emitted, want = 0, max(1, min(first, block))
-    while emitted < num_iterations:
-        alive = t.is_alive()
-        ready = min(int(progress.value), num_iterations)
-        if failure:
-            t.join()
-            raise failure[0]
-        if not alive and not failure and ready < num_iterations:
-            ready = num_iterations  # the Python fallback sampler finished without the counter
-        take = min(ready - emitted, block)
-        if ready < num_iterations:
-            take -= take % 10
-        if take >= min(want, num_iterations - emitted) and take > 0:
-            yield sched[emitted:emitted + take]
-            emitted += take
-            want = 10
-        else:
-            time.sleep(0.0005)
-    t.join()
+    try:
+        emitted, want = 0, max(1, min(first, block))
+        while emitted < num_iterations:
+            alive = t.is_alive()
+            ready = min(int(progress.value), num_iterations)
+            if failure:
+                raise failure[0]
+            if not alive and ready < num_iterations:
+                ready = num_iterations  # a sampler that finished without moving the counter
+            take = min(ready - emitted, block)
+            if ready < num_iterations:
+                take -= take % 10
+            if take >= min(want, num_iterations - emitted) and take > 0:
+                yield sched[emitted:emitted + take]
+                emitted += take
+                want = 10
+            else:
+                time.sleep(0.0005)
+    finally:
+        # also when the consumer gives up early: the sampler call runs to its end and restores numpy's generator state
+        # before control returns to the caller, never behind its back
+        t.join()
     if failure:
         raise failure[0]
 
