@@ -384,3 +384,18 @@ def test_whole_grid_split_operand_vs_fp32_path():
     assert (a - b).abs().max().item() <= 1e-4
     flips = (a > 0) != (b > 0)
     assert not (flips & (a.abs() > 5e-5)).any()
+
+
+@pytest.mark.parametrize("precision", ["fp16x2", "bf16"])
+def test_output_is_independent_of_the_position_in_the_batch(precision):
+    """A point's value must not depend on which tile, TMEM lane or CTA of a pair it lands in: shuffling the batch
+    (ragged size: the last tile is partial) permutes the outputs bit for bit."""
+    dec = util.make_decoder(0, "trained_norm", precision=precision)
+    code = util.trained_code(0).cuda()
+    pts = synth.make_points(7777, 11).cuda()
+    g = torch.Generator(device="cpu").manual_seed(3)
+    perm = torch.randperm(pts.shape[0], generator=g).cuda()
+    for u in (1, 3):
+        a = dec.query(code, pts, use_net=u)
+        b = dec.query(code, pts[perm].contiguous(), use_net=u)
+        assert torch.equal(a[perm], b)
